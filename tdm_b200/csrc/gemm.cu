@@ -1,0 +1,389 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with a fused epilogue (see include/tdm_b200.h: TdmGemm).
+//
+// One persistent CTA per SM, 256 threads, warp-specialised:
+//   warp 0   : TMA producer  (one lane) -- fills a ring of {A 128x64, B BNx64} bf16 stages (SW128)
+//   warp 1   : MMA issuer    (one lane) -- tcgen05.mma 128xBNx16 into one of two TMEM accumulators
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      -- tcgen05.ld (thread == accumulator row) -> fused math -> global
+// Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
+// Tails in M, N and K are handled by TMA out-of-bounds zero fill plus predicated stores.
+#include <stdio.h>
+#include "common.cuh"
+
+namespace tdm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+
+struct GemmParams {
+  int M, N, K, K2;
+  int a_mn, b_mn;
+  int seg_n, seg_k2;
+  int num_m_tiles, num_n_tiles;
+  float alpha;
+  int act;
+  const float* bias;
+  const bf16* act_in;
+  long ld_act;
+  bf16* pre_out;
+  long ld_pre;
+  const float* gate;
+  int rows_per_gate;
+  long gate_stride;
+  const float* res;
+  long ld_res;
+  float* out_f32;
+  long ld_out_f32;
+  bf16* out_bf16;
+  long ld_out_bf16;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nk1 = (p.K + BK - 1) / BK;
+  const int nk2 = (p.K2 + BK - 1) / BK;
+  const int nk = nk1 + nk2;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (nk2) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / p.num_n_tiles) * BM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int seg = p.seg_n > 0 ? n0 / p.seg_n : 0;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const CUtensorMap* mA = &tmA;
+          const CUtensorMap* mB = &tmB;
+          int ka = kb * BK, kbb = kb * BK;
+          if (kb >= nk1) {
+            mA = &tmA2;
+            mB = &tmB2;
+            kbb = (kb - nk1) * BK;
+            ka = seg * p.seg_k2 + kbb;
+          }
+          if (!p.a_mn) {
+            tma_load_2d(sA, mA, &full_bar[stage], ka, m0);
+          } else {
+            tma_load_2d(sA, mA, &full_bar[stage], m0, ka);
+            tma_load_2d(sA + 8192, mA, &full_bar[stage], m0 + 64, ka);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sB, mB, &full_bar[stage], kbb, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, mB, &full_bar[stage], n0 + 64 * j, kbb);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 along K
+      const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: TMEM lane quarter this warp may read
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / p.num_n_tiles) * BM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      const int m = m0 + ew * 32 + lane;
+      const bool row_ok = m < p.M;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * BN + (uint32_t(ew * 32) << 16);
+      const float* gate_row = nullptr;
+      if (p.gate && row_ok) gate_row = p.gate + (long)(m / p.rows_per_gate) * p.gate_stride;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (n0 + c >= p.N) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(taddr + c, acc);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int n = n0 + c + g * 8;
+            if (n < p.N) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(acc[g * 8 + i]);
+              if (p.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (p.pre_out) {
+                uint4 o;
+                o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(p.pre_out + (long)m * p.ld_pre + n) = o;
+              }
+              if (p.act == TDM_ACT_GELU_TANH) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
+              } else if (p.act == TDM_ACT_GELU_TANH_BWD) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+                const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+                v[0] *= gelu_tanh_grad(u0.x); v[1] *= gelu_tanh_grad(u0.y);
+                v[2] *= gelu_tanh_grad(u1.x); v[3] *= gelu_tanh_grad(u1.y);
+                v[4] *= gelu_tanh_grad(u2.x); v[5] *= gelu_tanh_grad(u2.y);
+                v[6] *= gelu_tanh_grad(u3.x); v[7] *= gelu_tanh_grad(u3.y);
+              }
+              if (gate_row) {
+                const float4 g0 = *reinterpret_cast<const float4*>(gate_row + n);
+                const float4 g1 = *reinterpret_cast<const float4*>(gate_row + n + 4);
+                v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+                v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+              }
+              if (p.res) {
+                const float4 r0 = *reinterpret_cast<const float4*>(p.res + (long)m * p.ld_res + n);
+                const float4 r1 = *reinterpret_cast<const float4*>(p.res + (long)m * p.ld_res + n + 4);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+                v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+              }
+              if (p.out_f32) {
+                float* o = p.out_f32 + (long)m * p.ld_out_f32 + n;
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
+              if (p.out_bf16) {
+                uint4 o;
+                o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+                o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+                *reinterpret_cast<uint4*>(p.out_bf16 + (long)m * p.ld_out_bf16 + n) = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, long rows_mn, long k, long ld,
+                            int box_mn) {
+  // K-major: stored [rows_mn, k], inner = k.  MN-major: stored [k, rows_mn], inner = rows_mn.
+  uint64_t dims[2], strides[1];
+  uint32_t box[2];
+  if (!mn_major) {
+    dims[0] = (uint64_t)k;
+    dims[1] = (uint64_t)rows_mn;
+    box[0] = BK;
+    box[1] = (uint32_t)box_mn;
+  } else {
+    dims[0] = (uint64_t)rows_mn;
+    dims[1] = (uint64_t)k;
+    box[0] = 64;
+    box[1] = BK;
+  }
+  strides[0] = (uint64_t)ld * 2;
+  return make_tma_bf16(map, ptr, 2, dims, strides, box, TMA_SWZ_128);
+}
+
+template <int BN>
+static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int rc;
+  if ((rc = make_operand_map(&tmA, g->A, g->a_mn_major, g->M, g->K, g->lda, BM))) return rc;
+  if ((rc = make_operand_map(&tmB, g->B, g->b_mn_major, g->N, g->K, g->ldb, BN))) return rc;
+  if (g->K2 > 0) {
+    const long a2_cols = g->seg_n > 0 ? (long)((g->N + g->seg_n - 1) / g->seg_n) * g->seg_k2 : g->K2;
+    if ((rc = make_operand_map(&tmA2, g->A2, g->a_mn_major, g->M, a2_cols, g->lda2, BM))) return rc;
+    if ((rc = make_operand_map(&tmB2, g->B2, g->b_mn_major, g->N, g->K2, g->ldb2, BN))) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+  GemmParams p;
+  p.M = g->M; p.N = g->N; p.K = g->K; p.K2 = g->K2 > 0 ? g->K2 : 0;
+  p.a_mn = g->a_mn_major; p.b_mn = g->b_mn_major;
+  p.seg_n = g->seg_n; p.seg_k2 = g->seg_k2;
+  p.num_m_tiles = (g->M + BM - 1) / BM;
+  p.num_n_tiles = (g->N + BN - 1) / BN;
+  p.alpha = g->alpha; p.act = g->act; p.bias = g->bias;
+  p.act_in = (const bf16*)g->act_in; p.ld_act = g->ld_act;
+  p.pre_out = (bf16*)g->pre_out; p.ld_pre = g->ld_pre;
+  p.gate = g->gate; p.rows_per_gate = g->rows_per_gate > 0 ? g->rows_per_gate : 1; p.gate_stride = g->gate_stride;
+  p.res = g->res; p.ld_res = g->ld_res;
+  p.out_f32 = g->out_f32; p.ld_out_f32 = g->ld_out_f32;
+  p.out_bf16 = (bf16*)g->out_bf16; p.ld_out_bf16 = g->ld_out_bf16;
+
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int sms = num_sms();
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_bf16_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  TDM_CHECK_CUDA(cudaGetLastError());
+  return TDM_OK;
+}
+
+}  // namespace tdm
+
+using namespace tdm;
+
+extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
+  TDM_REQUIRE(g != nullptr, "tdm_gemm_bf16: null descriptor");
+  TDM_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "tdm_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", g->M,
+              g->N, g->K);
+  TDM_REQUIRE(g->A && g->B, "tdm_gemm_bf16: A and B are required");
+  TDM_REQUIRE(g->out_f32 || g->out_bf16 || g->pre_out, "tdm_gemm_bf16: no output given");
+  TDM_REQUIRE(g->N % 8 == 0, "tdm_gemm_bf16: N=%d must be a multiple of 8", g->N);
+  TDM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "tdm_gemm_bf16: lda/ldb must be multiples of 8");
+  TDM_REQUIRE(((uintptr_t)g->A & 15) == 0 && ((uintptr_t)g->B & 15) == 0, "tdm_gemm_bf16: A/B must be 16-byte aligned");
+  TDM_REQUIRE(g->act == TDM_ACT_NONE || g->act == TDM_ACT_GELU_TANH || g->act == TDM_ACT_GELU_TANH_BWD,
+              "tdm_gemm_bf16: unknown act %d", g->act);
+  TDM_REQUIRE(g->act != TDM_ACT_GELU_TANH_BWD || g->act_in, "tdm_gemm_bf16: GELU_TANH_BWD needs act_in");
+  if (g->K2 > 0) {
+    TDM_REQUIRE(g->A2 && g->B2, "tdm_gemm_bf16: K2>0 needs A2 and B2");
+    TDM_REQUIRE(g->lda2 % 8 == 0 && g->ldb2 % 8 == 0, "tdm_gemm_bf16: lda2/ldb2 must be multiples of 8");
+    if (g->seg_n > 0)
+      TDM_REQUIRE(g->seg_k2 % 64 == 0 && g->K2 <= g->seg_k2, "tdm_gemm_bf16: segmented pair needs seg_k2 %% 64 == 0 and K2 <= seg_k2");
+  }
+  TDM_REQUIRE((!g->out_f32 || g->ld_out_f32 % 4 == 0) && (!g->out_bf16 || g->ld_out_bf16 % 8 == 0) &&
+                  (!g->res || g->ld_res % 4 == 0) && (!g->pre_out || g->ld_pre % 8 == 0) &&
+                  (!g->act_in || g->ld_act % 8 == 0) && (!g->gate || g->gate_stride % 4 == 0),
+              "tdm_gemm_bf16: epilogue leading dimensions must keep 16-byte alignment");
+  int bn = g->tile_n;
+  if (bn == 0) {
+    // Prefer the widest tile whose wave quantisation on this device stays good.
+    const int sms = num_sms();
+    const long mt = (g->M + BM - 1) / BM;
+    auto eff = [&](int b) {
+      const long t = mt * ((g->N + b - 1) / b);
+      const long waves = (t + sms - 1) / sms;
+      const double util = double(g->N) / double(((g->N + b - 1) / b) * b);  // padding waste in N
+      return util * double(t) / double(waves * sms);
+    };
+    const double e256 = eff(256), e128 = eff(128), e64 = eff(64);
+    bn = 256;
+    if (e128 > e256 * 1.04) bn = 128;
+    if (g->N <= 64 || (e64 > (bn == 256 ? e256 : e128) * 1.15)) bn = 64;
+    if (g->seg_n > 0 && g->seg_n % bn != 0) bn = (g->seg_n % 128 == 0) ? 128 : 64;
+  }
+  if (g->seg_n > 0) TDM_REQUIRE(g->seg_n % bn == 0, "tdm_gemm_bf16: seg_n=%d must be a multiple of tile_n=%d", g->seg_n, bn);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (bn) {
+    case 64: return launch_gemm<64>(g, s);
+    case 128: return launch_gemm<128>(g, s);
+    case 256: return launch_gemm<256>(g, s);
+    default: return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: tile_n must be 0, 64, 128 or 256 (got %d)", bn);
+  }
+}

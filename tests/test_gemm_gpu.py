@@ -1,0 +1,120 @@
+"""tcgen05 GEMM (tdm_gemm_bf16) against a torch fp32 reference of the same contraction + epilogue.
+
+Floating-point kernel: inputs are bf16, accumulation fp32; tolerance is stated per test."""
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+
+def _mk(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _close(got, ref, tol, what=""):
+    err = (got.float() - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-12
+    assert err / den <= tol, f"{what}: max abs err {err:.4g} / max ref {den:.4g} = {err/den:.3g} > {tol}"
+
+
+@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_majors(tile_n, a_mn, b_mn):
+    from tdm_b200 import ops
+    M, N, K = 384, 512, 320
+    a = _mk((M, K), seed=1)
+    b = _mk((N, K), seed=2)
+    ref = a.float() @ b.float().t()
+    a_s = a.t().contiguous() if a_mn else a
+    b_s = b.t().contiguous() if b_mn else b
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a_s, b_s, a_mn_major=a_mn, b_mn_major=b_mn, out_f32=out, tile_n=tile_n)
+    torch.cuda.synchronize()
+    _close(out, ref, 1e-5 * K ** 0.5 + 1e-4, f"majors a_mn={a_mn} b_mn={b_mn} bn={tile_n}")
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 72, 40), (8192, 1152, 1152), (960, 2304, 1152), (130, 264, 4096), (512, 32, 256)])
+def test_gemm_shapes_and_tails(M, N, K):
+    from tdm_b200 import ops
+    a = _mk((M, K), seed=3)
+    b = _mk((N, K), 0.05, seed=4)
+    ref = a.float() @ b.float().t()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out_bf16=out)
+    torch.cuda.synchronize()
+    _close(out, ref, 6e-3, f"shape {M}x{N}x{K}")  # bf16 output rounding 2^-8
+
+
+def test_gemm_epilogue_full():
+    from tdm_b200 import ops
+    B, T, N, K = 3, 200, 256, 192
+    M = B * T
+    a = _mk((M, K), seed=5)
+    w = _mk((N, K), 0.1, seed=6)
+    bias = torch.randn(N, device="cuda")
+    gate = torch.randn(B, 6 * N, device="cuda")[:, N:2 * N]  # strided view like a chunk of [B,6,D]
+    res = torch.randn(M, N, device="cuda")
+    pre = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, act=ops.ACT_GELU_TANH, pre_out=pre, gate=gate, rows_per_gate=T, res=res,
+             out_f32=o32, out_bf16=o16, alpha=0.5)
+    torch.cuda.synchronize()
+    v = 0.5 * (a.float() @ w.float().t()) + bias
+    _close(pre, v, 6e-3, "pre_out")
+    ref = torch.nn.functional.gelu(v, approximate="tanh") * gate.repeat_interleave(T, 0) + res
+    _close(o32, ref, 2e-4, "out_f32")
+    _close(o16, ref, 6e-3, "out_bf16")
+
+
+def test_gemm_gelu_bwd_and_accumulate():
+    from tdm_b200 import ops
+    M, N, K = 256, 384, 128
+    dy = _mk((M, K), seed=7)
+    w = _mk((K, N), 0.1, seed=8)       # stored [N_out=K, K_in=N]: dgrad reads it MN-major
+    u = _mk((M, N), seed=9)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, w, b_mn_major=True, act=ops.ACT_GELU_TANH_BWD, act_in=u, out_bf16=out)
+    uf = u.float().requires_grad_(True)
+    torch.nn.functional.gelu(uf, approximate="tanh").backward(dy.float() @ w.float())
+    _close(out, uf.grad, 6e-3, "gelu bwd dgrad")
+    # in-place accumulate: res aliases out_f32
+    acc = torch.randn(M, N, device="cuda")
+    ref = acc + dy.float() @ w.float()
+    ops.gemm(dy, w, b_mn_major=True, res=acc, out_f32=acc)
+    torch.cuda.synchronize()
+    _close(acc, ref, 2e-4, "accumulate")
+
+
+def test_gemm_lora_pair_and_segments():
+    from tdm_b200 import ops
+    M, D, r = 300, 128, 64
+    x = _mk((M, D), seed=10)
+    w = _mk((3 * D, D), 0.1, seed=11)
+    t = _mk((M, 3 * r), seed=12)            # x A^T for q,k,v
+    bl = _mk((3 * D, r), 0.1, seed=13)      # stacked B_q;B_k;B_v
+    out = torch.empty(M, 3 * D, device="cuda")
+    ops.gemm(x, w, a2=t, b2=bl, seg_n=D, seg_k2=r, out_f32=out)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t()
+    for s in range(3):
+        ref[:, s * D:(s + 1) * D] += t[:, s * r:(s + 1) * r].float() @ bl[s * D:(s + 1) * D].float().t()
+    _close(out, ref, 2e-4, "segmented LoRA pair")
+    # plain (unsegmented) pair with K2 = 16 (< one k-block: TMA zero-fills the rest)
+    t2 = _mk((M, 16), seed=14)
+    b2 = _mk((D, 16), 0.1, seed=15)
+    out2 = torch.empty(M, D, device="cuda")
+    ops.gemm(x, w[:D], a2=t2, b2=b2, out_f32=out2)
+    torch.cuda.synchronize()
+    _close(out2, x.float() @ w[:D].float().t() + t2.float() @ b2.float().t(), 2e-4, "rank-16 pair")
+
+
+def test_gemm_rejects_bad_args():
+    from tdm_b200 import ops, _lib
+    a = _mk((64, 64))
+    b = _mk((60, 64))
+    with pytest.raises(_lib.TdmError):
+        ops.gemm(a, b, out_f32=torch.empty(64, 60, device="cuda"))  # N % 8 != 0
+    with pytest.raises(_lib.TdmError):
+        ops.gemm(a, _mk((64, 64)))  # no output
