@@ -1,0 +1,315 @@
+// Flash attention backward on tcgen05 / TMEM (head_dim <= 128), self- and cross-attention.
+// One CTA owns a tile of 128 keys of one (batch, head) and loops over the query tiles:
+//   S^T  = K Q^T          (recomputed)        dP^T = V dO^T
+//   P^T  = exp(S^T*scale + bias - lse)        dS^T = P^T o (dP^T - delta)
+//   dV  += P^T dO         dK += dS^T Q        dQ  = dS K   (fp32 atomics into a [B,Sq,H,d] scratch)
+// thread == key row == TMEM lane for the softmax recompute; thread == query row for the dQ drain.
+// Operand reuse without copies: the Q / dO tiles are read K-major for S^T / dP^T and MN-major for
+// dK / dV; dS^T in shared memory is read K-major for dK and MN-major (as dS) for dQ.
+// TMEM: S^T [0,128) (reused for dQ), dP^T [128,256), dV [256,384), dK [384,512).
+#include "common.cuh"
+
+namespace tdm {
+
+constexpr int CHUNK = 128 * 128;  // bytes of one [128 rows x 64 bf16] swizzled chunk
+
+int make_head_map(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
+                  long stride_h);
+
+struct AttnBwdParams {
+  int B, H, Sq, Sk, d, nd, dk16;
+  float scale, scale_log2;
+  const float* bias;   // [B, Sk] or null
+  const float* lse;    // [B, H, Sq]
+  const float* delta;  // [B, H, Sq]
+  float* dq_accum;     // fp32 [B, Sq, H, d] contiguous
+  bf16* dK;
+  long dk_stride_b, dk_stride_s, dk_stride_h;
+  bf16* dV;
+  long dv_stride_b, dv_stride_s, dv_stride_h;
+};
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+__global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, long sb, long ss, long sh,
+                                  float* __restrict__ delta, int B, int H, int Sq, int d) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long total = (long)B * Sq * H;
+  if (idx >= total) return;
+  const int h = int(idx % H);
+  const int q = int((idx / H) % Sq);
+  const int b = int(idx / ((long)H * Sq));
+  const long off = (long)b * sb + (long)q * ss + (long)h * sh;
+  float acc = 0.f;
+  for (int c = 0; c < d; c += 8) {
+    const uint4 o = *reinterpret_cast<const uint4*>(O + off + c);
+    const uint4 g = *reinterpret_cast<const uint4*>(dO + off + c);
+    const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y), o2 = unpack_bf16(o.z), o3 = unpack_bf16(o.w);
+    const float2 g0 = unpack_bf16(g.x), g1 = unpack_bf16(g.y), g2 = unpack_bf16(g.z), g3 = unpack_bf16(g.w);
+    acc += o0.x * g0.x + o0.y * g0.y + o1.x * g1.x + o1.y * g1.y + o2.x * g2.x + o2.y * g2.y + o3.x * g3.x + o3.y * g3.y;
+  }
+  delta[((long)b * H + h) * Sq + q] = acc;
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tile_bytes = p.nd * CHUNK;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + tile_bytes;
+  uint8_t* sQ = sV + tile_bytes;
+  uint8_t* sdO = sQ + tile_bytes;
+  uint8_t* sPt = sdO + tile_bytes;   // [128 keys x 128 queries] bf16, 2 chunks
+  uint8_t* sdSt = sPt + 2 * CHUNK;
+  float* sLse = reinterpret_cast<float*>(sdSt + 2 * CHUNK);  // 128 (log2 units)
+  float* sDelta = sLse + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 128);
+  uint64_t* kv_full = bars;
+  uint64_t* qdo_full = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* pds_full = bars + 3;   // 128 arrivals
+  uint64_t* mma_done = bars + 4;
+  uint64_t* dq_drained = bars + 5; // 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (p.Sq + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(mma_done, 1);
+    mbar_init(dq_drained, 128);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 384;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
+      for (int c = 0; c < p.nd; ++c) {
+        tma_load_4d(sK + c * CHUNK, &tmK, kv_full, c * 64, k0, h, b);
+        tma_load_4d(sV + c * CHUNK, &tmV, kv_full, c * 64, k0, h, b);
+      }
+      for (int i = 0; i < n_q; ++i) {
+        if (i > 0) mbar_wait(mma_done, (i - 1) & 1);  // Q/dO tiles of the previous iteration fully consumed
+        mbar_arrive_expect_tx(qdo_full, 2 * tile_bytes);
+        for (int c = 0; c < p.nd; ++c) {
+          tma_load_4d(sQ + c * CHUNK, &tmQ, qdo_full, c * 64, i * 128, h, b);
+          tma_load_4d(sdO + c * CHUNK, &tmdO, qdo_full, c * 64, i * 128, h, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const int nd64 = p.nd * 64;
+      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);    // S^T, dP^T : A K-major, B K-major
+      const uint32_t id_kmn = make_idesc_bf16(128, nd64, 0, 1);  // dV, dK    : A K-major, B MN-major
+      const uint32_t id_mnmn = make_idesc_bf16(128, nd64, 1, 1); // dQ        : A MN-major, B MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO);
+      const uint32_t aPt = smem_u32(sPt), adSt = smem_u32(sdSt);
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < n_q; ++i) {
+        mbar_wait(qdo_full, i & 1);
+        if (i > 0) mbar_wait(dq_drained, (i - 1) & 1);  // S^T columns are reused by dQ
+        tc_fence_after();
+        for (int k = 0; k < p.dk16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_St, make_sdesc_sw128(aK + off, 16, 1024), make_sdesc_sw128(aQ + off, 16, 1024), id_kk, k != 0);
+        }
+        for (int k = 0; k < p.dk16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_dPt, make_sdesc_sw128(aV + off, 16, 1024), make_sdesc_sw128(adO + off, 16, 1024), id_kk, k != 0);
+        }
+        umma_commit(s_full);
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // contraction over the 128 queries of this tile
+          const uint32_t offA = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_dV, make_sdesc_sw128(aPt + offA, 16, 1024), make_sdesc_sw128(adO + k * 2048, CHUNK, 1024),
+                    id_kmn, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t offA = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_dK, make_sdesc_sw128(adSt + offA, 16, 1024), make_sdesc_sw128(aQ + k * 2048, CHUNK, 1024),
+                    id_kmn, (i | k) != 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dQ = dS K: contraction over the 128 keys; A = dS^T read MN-major
+          umma_bf16(tm_St, make_sdesc_sw128(adSt + k * 2048, CHUNK, 1024), make_sdesc_sw128(aK + k * 2048, CHUNK, 1024),
+                    id_mnmn, k != 0);
+        }
+        umma_commit(mma_done);
+      }
+    }
+  } else {
+    // ===================== compute warps (128 threads) =====================
+    const int tid = threadIdx.x;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const int kv = k0 + tid;
+    float bias_l2 = 0.f;
+    if (kv >= p.Sk) bias_l2 = -INFINITY;
+    else if (p.bias) bias_l2 = p.bias[(long)b * p.Sk + kv] * LOG2E;
+    const long bh = (long)b * p.H + h;
+    for (int i = 0; i < n_q; ++i) {
+      const int q = i * 128 + tid;
+      sLse[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
+      sDelta[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      uint8_t* prow = sPt + tid * 128;
+      uint8_t* drow = sdSt + tid * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tm_St + lane_off + c * 32, rs);
+        tmem_ld32(tm_dPt + lane_off + c * 32, rp);
+        tmem_ld_wait();
+        float pv[32], ds[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float pj = exp2f(fmaf(__uint_as_float(rs[j]), p.scale_log2, bias_l2) - sLse[c * 32 + j]);
+          pv[j] = pj;
+          ds[j] = pj * (__uint_as_float(rp[j]) - sDelta[c * 32 + j]);
+        }
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int U = c * 4 + u4;
+          const int off = (U >> 3) * CHUNK + (((U & 7) ^ (tid & 7)) << 4);
+          uint4 w;
+          w.x = pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1]); w.y = pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+          w.z = pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5]); w.w = pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + off) = w;
+          w.x = pack_bf16(ds[u4 * 8 + 0], ds[u4 * 8 + 1]); w.y = pack_bf16(ds[u4 * 8 + 2], ds[u4 * 8 + 3]);
+          w.z = pack_bf16(ds[u4 * 8 + 4], ds[u4 * 8 + 5]); w.w = pack_bf16(ds[u4 * 8 + 6], ds[u4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(drow + off) = w;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // drain dQ for this query tile (thread == query row)
+      mbar_wait(mma_done, i & 1);
+      tc_fence_after();
+      float* dq_row = p.dq_accum + (((long)b * p.Sq + q) * p.H + h) * p.d;
+      for (int c = 0; c < p.d; c += 8) {
+        uint32_t r[8];
+        tmem_ld8(tm_St + lane_off + c, r);
+        tmem_ld_wait();
+        if (q < p.Sq) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(dq_row + c + j, __uint_as_float(r[j]) * p.scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_drained);
+    }
+    // epilogue: dV, dK for this key tile (thread == key row)
+    bf16* dv_row = p.dV + (long)b * p.dv_stride_b + (long)kv * p.dv_stride_s + (long)h * p.dv_stride_h;
+    bf16* dk_row = p.dK + (long)b * p.dk_stride_b + (long)kv * p.dk_stride_s + (long)h * p.dk_stride_h;
+    for (int c = 0; c < p.d; c += 8) {
+      uint32_t rv[8], rk[8];
+      tmem_ld8(tm_dV + lane_off + c, rv);
+      tmem_ld8(tm_dK + lane_off + c, rk);
+      tmem_ld_wait();
+      if (kv < p.Sk) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
+        w.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+        w.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
+        w.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+        *reinterpret_cast<uint4*>(dv_row + c) = w;
+        w.x = pack_bf16(__uint_as_float(rk[0]) * p.scale, __uint_as_float(rk[1]) * p.scale);
+        w.y = pack_bf16(__uint_as_float(rk[2]) * p.scale, __uint_as_float(rk[3]) * p.scale);
+        w.z = pack_bf16(__uint_as_float(rk[4]) * p.scale, __uint_as_float(rk[5]) * p.scale);
+        w.w = pack_bf16(__uint_as_float(rk[6]) * p.scale, __uint_as_float(rk[7]) * p.scale);
+        *reinterpret_cast<uint4*>(dk_row + c) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// fp32 [rows, cols] (ld_in) -> bf16 [rows, cols] (ld_out): dQ scratch -> its slot in the d(qkv) matrix
+__global__ void cast2d_f32_bf16_kernel(const float* in, long ld_in, bf16* out, long ld_out, int rows, int cols) {
+  const int c4 = cols / 4;
+  const long total = (long)rows * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = int(i / c4), c = int(i % c4) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + (long)r * ld_in + c);
+    uint2 w;
+    w.x = pack_bf16(v.x, v.y);
+    w.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + (long)r * ld_out + c) = w;
+  }
+}
+
+}  // namespace tdm
+
+using namespace tdm;
+
+extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
+  TDM_REQUIRE(a && a->Q && a->K && a->V && a->O && a->dO && a->lse && a->delta && a->dq_accum && a->dQ && a->dK && a->dV,
+              "tdm_attn_bwd: null input");
+  TDM_REQUIRE(a->d % 8 == 0 && a->d >= 16 && a->d <= 128, "tdm_attn_bwd: head_dim=%d must be a multiple of 8 in [16,128]", a->d);
+  TDM_REQUIRE(a->dq_stride_h == a->d && a->dq_stride_b == (int64_t)a->Sq * a->dq_stride_s && a->dq_stride_s % 4 == 0,
+              "tdm_attn_bwd: dQ must be a [B*Sq, >=H*d] token matrix view");
+  cudaStream_t s = (cudaStream_t)stream;
+  CUtensorMap tmQ, tmK, tmV, tmdO;
+  int rc;
+  if ((rc = make_head_map(&tmQ, a->Q, a->B, a->Sq, a->H, a->d, a->q_stride_b, a->q_stride_s, a->q_stride_h))) return rc;
+  if ((rc = make_head_map(&tmK, a->K, a->B, a->Sk, a->H, a->d, a->k_stride_b, a->k_stride_s, a->k_stride_h))) return rc;
+  if ((rc = make_head_map(&tmV, a->V, a->B, a->Sk, a->H, a->d, a->v_stride_b, a->v_stride_s, a->v_stride_h))) return rc;
+  if ((rc = make_head_map(&tmdO, a->dO, a->B, a->Sq, a->H, a->d, a->o_stride_b, a->o_stride_s, a->o_stride_h))) return rc;
+  const long rows = (long)a->B * a->Sq;
+  const int HD = a->H * a->d;
+  {
+    const long total = rows * a->H;
+    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const bf16*)a->O, (const bf16*)a->dO, a->o_stride_b,
+                                                                     a->o_stride_s, a->o_stride_h, a->delta, a->B, a->H,
+                                                                     a->Sq, a->d);
+  }
+  TDM_CHECK_CUDA(cudaMemsetAsync(a->dq_accum, 0, sizeof(float) * rows * HD, s));
+  AttnBwdParams p;
+  p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d;
+  p.nd = (a->d + 63) / 64; p.dk16 = (a->d + 15) / 16;
+  p.scale = a->scale; p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.bias = a->bias; p.lse = a->lse; p.delta = a->delta; p.dq_accum = a->dq_accum;
+  p.dK = (bf16*)a->dK; p.dk_stride_b = a->dk_stride_b; p.dk_stride_s = a->dk_stride_s; p.dk_stride_h = a->dk_stride_h;
+  p.dV = (bf16*)a->dV; p.dv_stride_b = a->dv_stride_b; p.dv_stride_s = a->dv_stride_s; p.dv_stride_h = a->dv_stride_h;
+  const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 grid((a->Sk + 127) / 128, a->H, a->B);
+  attn_bwd_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+  TDM_CHECK_CUDA(cudaGetLastError());
+  // dQ scratch [B*Sq, H*d] fp32 -> bf16 dQ with the caller's strides (requires the [tokens, H*d] layout)
+  const int nblk = num_sms() * 8;
+  cast2d_f32_bf16_kernel<<<nblk, 256, 0, s>>>(a->dq_accum, HD, (bf16*)a->dQ, a->dq_stride_s, (int)rows, HD);
+  TDM_CHECK_CUDA(cudaGetLastError());
+  return TDM_OK;
+}

@@ -1,0 +1,291 @@
+// Flash attention forward on tcgen05 / TMEM for head_dim <= 128 (PixArt: 72), self- and cross-attention.
+// Replaces xformers.memory_efficient_attention (reference main.py:177-178, 372) inside the diffusers
+// Attention processor:  O = softmax(Q K^T * scale + bias) V,  bias = (1 - mask) * -10000 broadcast over
+// heads and queries.
+//
+// One CTA per (128 queries, head, batch); 192 threads:
+//   warps 0-3 : softmax + O correction + epilogue (thread == query row == TMEM lane)
+//   warp 4    : TMA producer (Q once, K/V tiles of 128 keys double-buffered)
+//   warp 5    : MMA issuer  (S = Q K^T into a ping-pong TMEM buffer, O += P V)
+// head_dim 72 is not a multiple of 64: every tile is loaded as ceil(d/64) 128-byte-swizzled column
+// chunks straight from the [tokens, heads*d] activation matrix with a 4-D tensor map (d, S, H, B);
+// TMA zero-fills columns >= d and rows >= S, so no padded copy of Q/K/V ever exists in HBM.
+#include "common.cuh"
+
+namespace tdm {
+
+constexpr int ATT_BM = 128;  // queries per CTA
+constexpr int ATT_BN = 128;  // keys per tile
+constexpr int CHUNK_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled chunk
+
+struct AttnFwdParams {
+  int B, H, Sq, Sk, d;
+  int nd;         // ceil(d / 64) column chunks
+  int dk16;       // ceil(d / 16) MMA k-steps for Q K^T
+  float scale_log2;  // softmax scale * log2(e)
+  const float* bias; // [B, Sk] additive, or null
+  bf16* O;        // [B, Sq, H, d] with strides
+  long o_stride_b, o_stride_s, o_stride_h;
+  float* lse;     // [B, H, Sq] natural-log sum-exp (for backward), or null
+};
+
+__device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
+  uint32_t r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(v[i]);
+  tmem_st8(taddr, r);
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int tile_bytes = p.nd * CHUNK_BYTES;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + tile_bytes;           // 2 stages
+  uint8_t* sV = sK + 2 * tile_bytes;       // 2 stages
+  uint8_t* sP = sV + 2 * tile_bytes;       // [128 x 128] bf16 = 2 chunks
+  float* sBias = reinterpret_cast<float*>(sP + 2 * CHUNK_BYTES);  // 2 x 128 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* kv_empty = bars + 5;  // [2]
+  uint64_t* s_full = bars + 7;    // [2]
+  uint64_t* p_full = bars + 9;
+  uint64_t* pv_done = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = (p.Sk + ATT_BN - 1) / ATT_BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
+  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_arrive_expect_tx(q_full, tile_bytes);
+      for (int c = 0; c < p.nd; ++c) tma_load_4d(sQ + c * CHUNK_BYTES, &tmQ, q_full, c * 64, q0, h, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], tile_bytes);
+        for (int c = 0; c < p.nd; ++c)
+          tma_load_4d(sK + st * tile_bytes + c * CHUNK_BYTES, &tmK, &k_full[st], c * 64, j * ATT_BN, h, b);
+        mbar_arrive_expect_tx(&v_full[st], tile_bytes);
+        for (int c = 0; c < p.nd; ++c)
+          tma_load_4d(sV + st * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[st], c * 64, j * ATT_BN, h, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, p.nd * 64, 0, 1);  // B = V is MN-major (d contiguous)
+      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_base = smem_u32(sK + st * tile_bytes);
+        for (int k = 0; k < p.dk16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
+          umma_bf16(tmem_S + (j & 1) * 128, make_sdesc_sw128(q_base + off, 16, 1024),
+                    make_sdesc_sw128(k_base + off, 16, 1024), idesc_qk, k != 0);
+        }
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < n_kv; ++j) {
+        if (j + 1 < n_kv) issue_qk(j + 1);
+        const int st = j & 1;
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[st], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t v_base = smem_u32(sV + st * tile_bytes);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k) {
+          const uint64_t da = make_sdesc_sw128(p_base + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_sdesc_sw128(v_base + k * 2048, CHUNK_BYTES, 1024);
+          umma_bf16(tmem_O, da, db, idesc_pv, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue (128 threads) =====================
+    const int tid = threadIdx.x;  // query row within the tile, TMEM lane
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      {  // additive bias (pre-multiplied by log2 e) and the key-padding mask for this tile
+        const int kv = j * ATT_BN + tid;
+        float bv = 0.f;
+        if (kv >= p.Sk) bv = -INFINITY;
+        else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
+        sBias[buf * 128 + tid] = bv;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* bias_s = sBias + buf * 128;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(s_addr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(r[i]), p.scale_log2, bias_s[c * 32 + i]));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O and the P buffer are free again
+        tc_fence_after();
+        const float alpha = exp2f(m_run - m_new);
+        l_run *= alpha;
+        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // tcgen05.ld/st are warp-collective
+          for (int c = 0; c < p.d; c += 8) {
+            uint32_t r[8];
+            tmem_ld8(tmem_O + lane_off + c, r);
+            tmem_ld_wait();
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+            tmem_st8w(tmem_O + lane_off + c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      m_run = m_new;
+      uint8_t* prow = sP + tid * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(s_addr + c * 32, r);
+        tmem_ld_wait();
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, bias_s[c * 32 + i]) - m_new);
+          l_run += pv[i];
+        }
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int U = c * 4 + u4;  // 16-byte unit index within the 128-key row
+          uint4 w;
+          w.x = pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
+          w.y = pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
+          w.z = pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
+          w.w = pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
+          *reinterpret_cast<uint4*>(prow + (U >> 3) * CHUNK_BYTES + (((U & 7) ^ (tid & 7)) << 4)) = w;
+        }
+      }
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int q = q0 + tid;
+    const float inv_l = 1.f / l_run;
+    if (q < p.Sq) {
+      if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    }
+    bf16* orow = p.O + (long)b * p.o_stride_b + (long)q * p.o_stride_s + (long)h * p.o_stride_h;
+    for (int c = 0; c < p.d; c += 8) {
+      uint32_t r[8];
+      tmem_ld8(tmem_O + lane_off + c, r);
+      tmem_ld_wait();
+      if (q < p.Sq) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+        w.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+        w.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+        w.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
+        *reinterpret_cast<uint4*>(orow + c) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// 4-D tensor map over a [B, S, H, d] view (d contiguous) of a token matrix; box = 64 x 128 x 1 x 1.
+int make_head_map(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
+                  long stride_h) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)S, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)stride_s * 2, (uint64_t)stride_h * 2, (uint64_t)stride_b * 2};
+  uint32_t box[4] = {64, 128, 1, 1};
+  return make_tma_bf16(map, ptr, 4, dims, strides, box, TMA_SWZ_128);
+}
+
+}  // namespace tdm
+
+using namespace tdm;
+
+extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
+  TDM_REQUIRE(a && a->Q && a->K && a->V && a->O, "tdm_attn_fwd: null input");
+  TDM_REQUIRE(a->d % 8 == 0 && a->d >= 16 && a->d <= 128, "tdm_attn_fwd: head_dim=%d must be a multiple of 8 in [16,128]", a->d);
+  TDM_REQUIRE(a->B > 0 && a->H > 0 && a->Sq > 0 && a->Sk > 0, "tdm_attn_fwd: bad shape");
+  TDM_REQUIRE(a->q_stride_s % 8 == 0 && a->q_stride_h % 8 == 0 && a->q_stride_b % 8 == 0 &&
+                  a->k_stride_s % 8 == 0 && a->k_stride_h % 8 == 0 && a->k_stride_b % 8 == 0 &&
+                  a->v_stride_s % 8 == 0 && a->v_stride_h % 8 == 0 && a->v_stride_b % 8 == 0 &&
+                  a->o_stride_s % 8 == 0 && a->o_stride_h % 8 == 0 && a->o_stride_b % 8 == 0,
+              "tdm_attn_fwd: strides must be multiples of 8 elements (16 bytes)");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_head_map(&tmQ, a->Q, a->B, a->Sq, a->H, a->d, a->q_stride_b, a->q_stride_s, a->q_stride_h))) return rc;
+  if ((rc = make_head_map(&tmK, a->K, a->B, a->Sk, a->H, a->d, a->k_stride_b, a->k_stride_s, a->k_stride_h))) return rc;
+  if ((rc = make_head_map(&tmV, a->V, a->B, a->Sk, a->H, a->d, a->v_stride_b, a->v_stride_s, a->v_stride_h))) return rc;
+  AttnFwdParams p;
+  p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d;
+  p.nd = (a->d + 63) / 64;
+  p.dk16 = (a->d + 15) / 16;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.bias = a->bias;
+  p.O = (bf16*)a->O; p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
+  p.lse = a->lse;
+  const int smem = 5 * p.nd * CHUNK_BYTES + 2 * CHUNK_BYTES + 1024 + 256 + 1024;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
+  }
+  dim3 grid((a->Sq + ATT_BM - 1) / ATT_BM, a->H, a->B);
+  attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  TDM_CHECK_CUDA(cudaGetLastError());
+  return TDM_OK;
+}

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include "../../include/tdm_b200.h"
 

@@ -28,6 +28,9 @@ struct GemmParams {
   long ld_act;
   bf16* pre_out;
   long ld_pre;
+  float* pre_out_f32;
+  long ld_pre_f32;
+  int res_row_mod;
   const float* gate;
   int rows_per_gate;
   long gate_stride;
@@ -217,6 +220,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
                 *reinterpret_cast<uint4*>(p.pre_out + (long)m * p.ld_pre + n) = o;
               }
+              if (p.pre_out_f32) {
+                float* o = p.pre_out_f32 + (long)m * p.ld_pre_f32 + n;
+                *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+              }
               if (p.act == TDM_ACT_GELU_TANH) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = gelu_tanh(v[i]);
@@ -228,6 +236,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[4] *= gelu_tanh_grad(u2.x); v[5] *= gelu_tanh_grad(u2.y);
                 v[6] *= gelu_tanh_grad(u3.x); v[7] *= gelu_tanh_grad(u3.y);
               }
+              else if (p.act == TDM_ACT_SILU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+              } else if (p.act == TDM_ACT_SILU_BWD) {
+                const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+                const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+                const float uu[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const float sg = 1.f / (1.f + __expf(-uu[i]));
+                  v[i] *= sg * (1.f + uu[i] * (1.f - sg));
+                }
+              }
               if (gate_row) {
                 const float4 g0 = *reinterpret_cast<const float4*>(gate_row + n);
                 const float4 g1 = *reinterpret_cast<const float4*>(gate_row + n + 4);
@@ -235,8 +256,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
               }
               if (p.res) {
-                const float4 r0 = *reinterpret_cast<const float4*>(p.res + (long)m * p.ld_res + n);
-                const float4 r1 = *reinterpret_cast<const float4*>(p.res + (long)m * p.ld_res + n + 4);
+                const long rr = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
+                const float4 r0 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n);
+                const float4 r1 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n + 4);
                 v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
                 v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
               }
@@ -316,6 +338,7 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   p.alpha = g->alpha; p.act = g->act; p.bias = g->bias;
   p.act_in = (const bf16*)g->act_in; p.ld_act = g->ld_act;
   p.pre_out = (bf16*)g->pre_out; p.ld_pre = g->ld_pre;
+  p.pre_out_f32 = g->pre_out_f32; p.ld_pre_f32 = g->ld_pre_f32; p.res_row_mod = g->res_row_mod;
   p.gate = g->gate; p.rows_per_gate = g->rows_per_gate > 0 ? g->rows_per_gate : 1; p.gate_stride = g->gate_stride;
   p.res = g->res; p.ld_res = g->ld_res;
   p.out_f32 = g->out_f32; p.ld_out_f32 = g->ld_out_f32;
@@ -344,13 +367,13 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   TDM_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0, "tdm_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", g->M,
               g->N, g->K);
   TDM_REQUIRE(g->A && g->B, "tdm_gemm_bf16: A and B are required");
-  TDM_REQUIRE(g->out_f32 || g->out_bf16 || g->pre_out, "tdm_gemm_bf16: no output given");
+  TDM_REQUIRE(g->out_f32 || g->out_bf16 || g->pre_out || g->pre_out_f32, "tdm_gemm_bf16: no output given");
   TDM_REQUIRE(g->N % 8 == 0, "tdm_gemm_bf16: N=%d must be a multiple of 8", g->N);
   TDM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "tdm_gemm_bf16: lda/ldb must be multiples of 8");
   TDM_REQUIRE(((uintptr_t)g->A & 15) == 0 && ((uintptr_t)g->B & 15) == 0, "tdm_gemm_bf16: A/B must be 16-byte aligned");
-  TDM_REQUIRE(g->act == TDM_ACT_NONE || g->act == TDM_ACT_GELU_TANH || g->act == TDM_ACT_GELU_TANH_BWD,
-              "tdm_gemm_bf16: unknown act %d", g->act);
-  TDM_REQUIRE(g->act != TDM_ACT_GELU_TANH_BWD || g->act_in, "tdm_gemm_bf16: GELU_TANH_BWD needs act_in");
+  TDM_REQUIRE(g->act >= TDM_ACT_NONE && g->act <= TDM_ACT_SILU_BWD, "tdm_gemm_bf16: unknown act %d", g->act);
+  TDM_REQUIRE((g->act != TDM_ACT_GELU_TANH_BWD && g->act != TDM_ACT_SILU_BWD) || g->act_in,
+              "tdm_gemm_bf16: backward activations need act_in");
   if (g->K2 > 0) {
     TDM_REQUIRE(g->A2 && g->B2, "tdm_gemm_bf16: K2>0 needs A2 and B2");
     TDM_REQUIRE(g->lda2 % 8 == 0 && g->ldb2 % 8 == 0, "tdm_gemm_bf16: lda2/ldb2 must be multiples of 8");
@@ -359,6 +382,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   }
   TDM_REQUIRE((!g->out_f32 || g->ld_out_f32 % 4 == 0) && (!g->out_bf16 || g->ld_out_bf16 % 8 == 0) &&
                   (!g->res || g->ld_res % 4 == 0) && (!g->pre_out || g->ld_pre % 8 == 0) &&
+                  (!g->pre_out_f32 || g->ld_pre_f32 % 4 == 0) &&
                   (!g->act_in || g->ld_act % 8 == 0) && (!g->gate || g->gate_stride % 4 == 0),
               "tdm_gemm_bf16: epilogue leading dimensions must keep 16-byte alignment");
   int bn = g->tile_n;
