@@ -36,6 +36,8 @@ extern "C" {
 const char* tdm_last_error(void); /* thread-local, never NULL */
 int tdm_version(void);            /* ABI version, bumped on any signature change */
 int tdm_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches); reset != 0 zeroes it */
+uint64_t tdm_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------------
  * Dense contraction on the 5th-gen tensor cores (tcgen05.mma, TMEM accumulators, TMA-fed).
@@ -209,6 +211,27 @@ int tdm_scheduler_add_noise(const void* x0, int x0_dtype, const void* noise, int
 int tdm_solver_step_bwd(const float* g_eps, const float* g_x0, double cfg, int has_uncond, const int64_t* t,
                         const void* alphas, const void* sigmas, int table_dtype, int table_len, float* d_out_c,
                         float* d_out_u, int B, int C, int Cout, int HW, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Training-step glue (src/main.py:473-479, 535-540).  Device-side scalars only: nothing here syncs. */
+
+/* out[b] = states[index[b]][b]: `noisy_imgs_list[ind_t]` (main.py:479) as the per-sample gather it was
+ * meant to be; negative indices count from the end like Python's. */
+int tdm_select_states(const void* const* states, const int* state_dtypes, int n_states, const int64_t* index, void* out,
+                      int out_dtype, int B, long per_sample, void* stream);
+/* Fake-score denoising loss (repair of SURVEY.md D5; the reference never trains unet_fake, main.py:470-505):
+ * loss = mean((pred[:, :C] - target)^2) in fp64, grad_out[B,C,HW] = 2 (pred - target) / numel * grad_scale. */
+int tdm_mse_fwd_bwd(const float* pred, const float* target, double* loss_out, float* grad_out, float grad_scale, int B,
+                    int C, int Cout, int HW, void* stream);
+/* accelerator.clip_grad_norm_ (main.py:537) on flat gradient arenas: accumulate sum of squares, then
+ * coef = min(1, max_norm / (norm + 1e-6)) * inv_scale with norm = sqrt(sumsq) * inv_scale. */
+int tdm_sumsq_f32(const float* x, int64_t n, double* accum, int zero_first, void* stream);
+int tdm_clip_coef(const double* sumsq, float max_norm, float inv_scale, float* coef_out, float* norm_out, void* stream);
+/* optimizer.step() (main.py:206-224, 538): torch.optim.AdamW semantics on a flat fp32 arena; the gradient is
+ * multiplied by *grad_coef (device scalar, may be NULL); param_bf16 (optional) receives the re-cast weights. */
+int tdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_coef,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * One PixArt DiT block (diffusers BasicTransformerBlock, norm_type="ada_norm_single"; SURVEY.md

@@ -119,6 +119,7 @@ SIGNATURES = {
     "tdm_last_error": (C.c_char_p, []),
     "tdm_version": (ci, []),
     "tdm_device_info": (ci, [C.POINTER(ci)] * 3),
+    "tdm_launch_count": (C.c_uint64, [ci]),
     "tdm_gemm_bf16": (ci, [C.POINTER(TdmGemm), vp]),
     "tdm_attn_fwd": (ci, [C.POINTER(TdmAttn), vp]),
     "tdm_attn_bwd": (ci, [C.POINTER(TdmAttn), vp]),
@@ -138,6 +139,11 @@ SIGNATURES = {
     "tdm_cast_f32_bf16": (ci, [vp, vp, i64, vp]),
     "tdm_scheduler_add_noise": (ci, [vp, ci, vp, ci, vp, vp, ci, vp, ci, ci, cl, vp]),
     "tdm_solver_step_bwd": (ci, [vp, vp, cd, ci, vp, vp, vp, ci, ci, vp, vp, ci, ci, ci, ci, vp]),
+    "tdm_select_states": (ci, [vp, vp, ci, vp, vp, ci, ci, cl, vp]),
+    "tdm_mse_fwd_bwd": (ci, [vp, vp, vp, vp, cf, ci, ci, ci, ci, vp]),
+    "tdm_sumsq_f32": (ci, [vp, i64, vp, ci, vp]),
+    "tdm_clip_coef": (ci, [vp, cf, cf, vp, vp, vp]),
+    "tdm_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, vp, vp]),
     "tdm_dit_block_ws_bytes": (i64, [C.POINTER(TdmDitShape), ci]),
     "tdm_dit_block_bwd_scratch_bytes": (i64, [C.POINTER(TdmDitShape)]),
     "tdm_dit_block_fwd": (ci, [C.POINTER(TdmDitShape), C.POINTER(TdmBlockWeights), vp, vp, vp, vp, vp, vp, ci, vp]),

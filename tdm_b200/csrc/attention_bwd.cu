@@ -286,7 +286,7 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   const int HD = a->H * a->d;
   {
     const long total = rows * a->H;
-    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const bf16*)a->O, (const bf16*)a->dO, a->o_stride_b,
+    ::tdm::count_launch(); attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const bf16*)a->O, (const bf16*)a->dO, a->o_stride_b,
                                                                      a->o_stride_s, a->o_stride_h, a->delta, a->B, a->H,
                                                                      a->Sq, a->d);
   }
@@ -305,11 +305,11 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
     smem_set = smem;
   }
   dim3 grid((a->Sk + 127) / 128, a->H, a->B);
-  attn_bwd_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+  ::tdm::count_launch(); attn_bwd_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   // dQ scratch [B*Sq, H*d] fp32 -> bf16 dQ with the caller's strides (requires the [tokens, H*d] layout)
   const int nblk = num_sms() * 8;
-  cast2d_f32_bf16_kernel<<<nblk, 256, 0, s>>>(a->dq_accum, HD, (bf16*)a->dQ, a->dq_stride_s, (int)rows, HD);
+  ::tdm::count_launch(); cast2d_f32_bf16_kernel<<<nblk, 256, 0, s>>>(a->dq_accum, HD, (bf16*)a->dQ, a->dq_stride_s, (int)rows, HD);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -285,7 +285,7 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
     smem_set = smem;
   }
   dim3 grid((a->Sq + ATT_BM - 1) / ATT_BM, a->H, a->B);
-  attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  ::tdm::count_launch(); attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

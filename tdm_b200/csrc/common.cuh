@@ -31,6 +31,7 @@ int set_error(int code, const char* fmt, ...);
   } while (0)
 
 int num_sms();  // cached multiprocessor count of the current device
+void count_launch();  // bumps the library-wide kernel launch counter (tdm_launch_count)
 
 // TMA tensor maps are built on the host per launch (pure host arithmetic, ~1 us).
 // rank <= 4; dims/strides innermost first; strides in bytes for dims 1..rank-1.

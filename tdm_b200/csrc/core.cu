@@ -17,6 +17,14 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
+unsigned long long launches(int reset) {
+  unsigned long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_launches, 0ull, __ATOMIC_RELAXED);
+  return v;
+}
+
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;
@@ -79,7 +87,8 @@ int make_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 }  // namespace tdm
 
 extern "C" const char* tdm_last_error(void) { return tdm::g_err; }
-extern "C" int tdm_version(void) { return 1; }
+extern "C" int tdm_version(void) { return 2; }
+extern "C" uint64_t tdm_launch_count(int reset) { return tdm::launches(reset); }
 extern "C" int tdm_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   int dev = 0;
   TDM_CHECK_CUDA(cudaGetDevice(&dev));

@@ -210,7 +210,7 @@ template <int MODE>
 static int launch_colreduce(ColRedArgs a, cudaStream_t s) {
   a.rows_per_block = pick_rows_per_block(a.rows_per_sample);
   dim3 grid((a.D + 127) / 128, (a.M + a.rows_per_block - 1) / a.rows_per_block);
-  colreduce_kernel<MODE><<<grid, dim3(32, 8), 0, s>>>(a);
+  ::tdm::count_launch(); colreduce_kernel<MODE><<<grid, dim3(32, 8), 0, s>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -341,7 +341,7 @@ extern "C" int tdm_ln_modulate_fwd(const float* x, const float* shift, const flo
   TDM_REQUIRE(x && shift && scale && out_bf16, "tdm_ln_modulate_fwd: null input");
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_fwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE(M > 0 && rows_per_sample > 0 && mod_stride % 4 == 0, "tdm_ln_modulate_fwd: bad shape");
-  ln_modulate_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, mod_stride, rows_per_sample,
+  ::tdm::count_launch(); ln_modulate_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, mod_stride, rows_per_sample,
                                                                       (bf16*)out_bf16, mean, rstd, M, D, eps);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
@@ -355,7 +355,7 @@ extern "C" int tdm_ln_modulate_bwd(const void* dh_bf16, const float* x, const fl
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_bwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE((dshift == nullptr) == (dscale == nullptr), "tdm_ln_modulate_bwd: dshift and dscale come together");
   cudaStream_t s = (cudaStream_t)stream;
-  ln_modulate_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>((const bf16*)dh_bf16, x, mean, rstd, scale, mod_stride,
+  ::tdm::count_launch(); ln_modulate_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>((const bf16*)dh_bf16, x, mean, rstd, scale, mod_stride,
                                                     rows_per_sample, dx_in, dx_out, (bf16*)dx_out_bf16, M, D);
   TDM_CHECK_CUDA(cudaGetLastError());
   if (dshift) {
@@ -391,7 +391,7 @@ extern "C" int tdm_colsum_bf16(const void* a_bf16, int64_t ld, int M, int N, flo
 extern "C" int tdm_modulation(const float* table, const float* tvec, int per_j, float* out, int B, int J, int D,
                               void* stream) {
   TDM_REQUIRE(table && tvec && out, "tdm_modulation: null input");
-  modulation_kernel<<<ew_grid((long)B * J * D, 256), 256, 0, (cudaStream_t)stream>>>(table, tvec, per_j, out, B, J, D);
+  ::tdm::count_launch(); modulation_kernel<<<ew_grid((long)B * J * D, 256), 256, 0, (cudaStream_t)stream>>>(table, tvec, per_j, out, B, J, D);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -399,7 +399,7 @@ extern "C" int tdm_modulation(const float* table, const float* tvec, int per_j, 
 extern "C" int tdm_modulation_bwd(const float* dmod, float* dtable, float* dtvec, int per_j, int accumulate_tvec,
                                   int B, int J, int D, void* stream) {
   TDM_REQUIRE(dmod, "tdm_modulation_bwd: null input");
-  modulation_bwd_kernel<<<ew_grid((long)J * D, 256), 256, 0, (cudaStream_t)stream>>>(dmod, dtable, dtvec, per_j,
+  ::tdm::count_launch(); modulation_bwd_kernel<<<ew_grid((long)J * D, 256), 256, 0, (cudaStream_t)stream>>>(dmod, dtable, dtvec, per_j,
                                                                                    accumulate_tvec, B, J, D);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
@@ -408,21 +408,21 @@ extern "C" int tdm_modulation_bwd(const float* dmod, float* dtable, float* dtvec
 extern "C" int tdm_timestep_sinusoid(const int64_t* t, void* out_bf16, int B, int dim, void* stream) {
   TDM_REQUIRE(t && out_bf16 && dim % 2 == 0, "tdm_timestep_sinusoid: bad input");
   const int n = B * dim / 2;
-  timestep_sinusoid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, (bf16*)out_bf16, B, dim);
+  ::tdm::count_launch(); timestep_sinusoid_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t, (bf16*)out_bf16, B, dim);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
 
 extern "C" int tdm_patchify(const void* latent, int dtype, void* out_bf16, int B, int C, int H, int W, int p, void* stream) {
   TDM_REQUIRE(latent && out_bf16 && H % p == 0 && W % p == 0, "tdm_patchify: bad input");
-  patchify_kernel<<<ew_grid((long)B * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(latent, dtype, (bf16*)out_bf16, B, C, H, W, p);
+  ::tdm::count_launch(); patchify_kernel<<<ew_grid((long)B * C * H * W, 256), 256, 0, (cudaStream_t)stream>>>(latent, dtype, (bf16*)out_bf16, B, C, H, W, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
 
 extern "C" int tdm_unpatchify(const float* y, int64_t ldy, float* out, int B, int Cout, int H, int W, int p, void* stream) {
   TDM_REQUIRE(y && out && H % p == 0 && W % p == 0, "tdm_unpatchify: bad input");
-  unpatchify_kernel<<<ew_grid((long)B * Cout * H * W, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, out, B, Cout, H, W, p);
+  ::tdm::count_launch(); unpatchify_kernel<<<ew_grid((long)B * Cout * H * W, 256), 256, 0, (cudaStream_t)stream>>>(y, ldy, out, B, Cout, H, W, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -430,7 +430,7 @@ extern "C" int tdm_unpatchify(const float* y, int64_t ldy, float* out, int B, in
 extern "C" int tdm_unpatchify_bwd(const float* dout, void* dy_bf16, int B, int Cgrad, int Cout, int H, int W, int p,
                                   void* stream) {
   TDM_REQUIRE(dout && dy_bf16 && Cgrad <= Cout, "tdm_unpatchify_bwd: bad input");
-  unpatchify_bwd_kernel<<<ew_grid((long)B * Cout * H * W, 256), 256, 0, (cudaStream_t)stream>>>(dout, (bf16*)dy_bf16, B, Cgrad, Cout, H, W, p);
+  ::tdm::count_launch(); unpatchify_bwd_kernel<<<ew_grid((long)B * Cout * H * W, 256), 256, 0, (cudaStream_t)stream>>>(dout, (bf16*)dy_bf16, B, Cgrad, Cout, H, W, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -438,7 +438,7 @@ extern "C" int tdm_unpatchify_bwd(const float* dout, void* dy_bf16, int B, int C
 extern "C" int tdm_cast_f32_bf16(const float* in, void* out_bf16, int64_t n, void* stream) {
   TDM_REQUIRE(in && out_bf16, "tdm_cast_f32_bf16: null input");
   TDM_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "tdm_cast_f32_bf16: misaligned");
-  cast_f32_bf16_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out_bf16, n);
+  ::tdm::count_launch(); cast_f32_bf16_kernel<<<ew_grid((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(in, (bf16*)out_bf16, n);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -353,7 +353,7 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int sms = num_sms();
   const int grid = tiles < sms ? tiles : sms;
-  gemm_bf16_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  ::tdm::count_launch(); gemm_bf16_kernel<BN><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -309,7 +309,7 @@ extern "C" int tdm_solver_step(const float* model_out, const float* model_out_un
   a.eps_out = eps_out; a.x0_out = x0_out; a.x_next = x_next; a.next_dt = next_dtype;
   a.B = B; a.C = C; a.Cout = Cout; a.HW = HW;
   const long total = (long)B * C * HW;
-  solver_step_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  ::tdm::count_launch(); solver_step_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -331,7 +331,7 @@ extern "C" int tdm_renoise(const void* const* states, const int* state_dtypes, i
   a.n_states = n_states; a.index = index; a.noise = noise; a.noise_dt = noise_dtype; a.t1 = t1; a.t2 = t2;
   a.alphas = alphas; a.sigmas = sigmas; a.table_dt = table_dtype; a.table_len = table_len; a.out = out;
   a.out_dt = out_dtype; a.mixed = mixed; a.per = per_sample; a.B = B;
-  renoise_kernel<<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  ::tdm::count_launch(); renoise_kernel<<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -353,8 +353,8 @@ extern "C" int tdm_loss_fwd_bwd(const float* model_latents, const float* sd_late
   int chunks = (int)((per_sample + 2047) / 2048);
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, B);
-  loss_weight_kernel<<<grid, 256, 0, s>>>(a);
-  loss_value_kernel<<<grid, 256, 0, s>>>(a);
+  ::tdm::count_launch(); loss_weight_kernel<<<grid, 256, 0, s>>>(a);
+  ::tdm::count_launch(); loss_value_kernel<<<grid, 256, 0, s>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -366,7 +366,7 @@ extern "C" int tdm_scheduler_add_noise(const void* x0, int x0_dtype, const void*
   TDM_REQUIRE(dt_ok(x0_dtype) && dt_ok(noise_dtype) && dt_ok(out_dtype), "tdm_scheduler_add_noise: bad dtype enum");
   const int want = x0_dtype == noise_dtype ? x0_dtype : TDM_F32;
   TDM_REQUIRE(out_dtype == want, "tdm_scheduler_add_noise: out dtype must be the promoted type (%d)", want);
-  sched_add_noise_kernel<<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(
+  ::tdm::count_launch(); sched_add_noise_kernel<<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(
       x0, x0_dtype, noise, noise_dtype, t, alphas_cumprod, table_len, out, out_dtype, per_sample, B);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
@@ -378,7 +378,7 @@ extern "C" int tdm_solver_step_bwd(const float* g_eps, const float* g_x0, double
   TDM_REQUIRE((g_eps || g_x0) && d_out_c && t && alphas && sigmas, "tdm_solver_step_bwd: null input");
   TDM_REQUIRE(!has_uncond || d_out_u, "tdm_solver_step_bwd: d_out_u required with an unconditional branch");
   TDM_REQUIRE(dt_ok(table_dtype), "tdm_solver_step_bwd: bad dtype enum");
-  solver_step_bwd_kernel<<<ew_grid((long)B * Cout * HW, 256), 256, 0, (cudaStream_t)stream>>>(
+  ::tdm::count_launch(); solver_step_bwd_kernel<<<ew_grid((long)B * Cout * HW, 256), 256, 0, (cudaStream_t)stream>>>(
       g_eps, g_x0, (float)cfg, has_uncond, t, alphas, sigmas, table_dtype, table_len, d_out_c,
       has_uncond ? d_out_u : nullptr, B, C, Cout, HW);
   TDM_CHECK_CUDA(cudaGetLastError());

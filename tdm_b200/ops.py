@@ -290,3 +290,52 @@ def cast_bf16(x):
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
     check(_lib.lib().tdm_cast_f32_bf16(ptr(x), ptr(out), x.numel(), stream_handle()))
     return out
+
+
+def select_states(states, index, out_dtype=None):
+    """out[b] = states[index[b]][b] (main.py:479 as a per-sample gather)."""
+    states = [s.contiguous() for s in states]
+    for s in states:
+        _cuda(s, "states")
+    B = states[0].shape[0]
+    per = states[0][0].numel()
+    out = torch.empty(states[0].shape, device=states[0].device, dtype=out_dtype or states[0].dtype)
+    arr_p = (C.c_void_p * len(states))(*[ptr(s) for s in states])
+    arr_d = (C.c_int * len(states))(*[_lib.dtype_enum(s) for s in states])
+    if index.dtype != torch.int64:
+        raise _lib.TdmError("index must be int64")
+    check(_lib.lib().tdm_select_states(C.cast(arr_p, C.c_void_p), C.cast(arr_d, C.c_void_p), len(states), ptr(index),
+                                       ptr(out), _lib.dtype_enum(out), B, per, stream_handle()))
+    return out
+
+
+def mse_loss(pred, target, want_grad=True, grad_scale=1.0):
+    """mean((pred[:, :C] - target)^2) -> (fp64 0-dim loss, grad [B,C,H,W] fp32 or None)."""
+    _req(pred, torch.float32, "pred"); _req(target, torch.float32, "target")
+    pred, target = pred.contiguous(), target.contiguous()
+    B, C_ = target.shape[0], target.shape[1]
+    HW = target[0, 0].numel()
+    loss = torch.empty((), device=pred.device, dtype=torch.float64)
+    grad = torch.empty_like(target) if want_grad else None
+    check(_lib.lib().tdm_mse_fwd_bwd(ptr(pred), ptr(target), ptr(loss), ptr(grad), float(grad_scale), B, C_,
+                                     pred.shape[1], HW, stream_handle()))
+    return loss, grad
+
+
+def sumsq(x, accum, zero_first):
+    _req(x, torch.float32, "x")
+    check(_lib.lib().tdm_sumsq_f32(ptr(x), x.numel(), ptr(accum), int(zero_first), stream_handle()))
+
+
+def clip_coef(sumsq_acc, max_norm, inv_scale, coef_out, norm_out=None):
+    check(_lib.lib().tdm_clip_coef(ptr(sumsq_acc), float(max_norm), float(inv_scale), ptr(coef_out), ptr(norm_out),
+                                   stream_handle()))
+
+
+def adamw_step(param, grad, exp_avg, exp_avg_sq, param_bf16, lr, beta1, beta2, eps, weight_decay, step, grad_coef=None):
+    for t, n in ((param, "param"), (grad, "grad"), (exp_avg, "exp_avg"), (exp_avg_sq, "exp_avg_sq")):
+        _req(t, torch.float32, n)
+    _req(param_bf16, torch.bfloat16, "param_bf16")
+    check(_lib.lib().tdm_adamw_step(ptr(param), ptr(grad), ptr(exp_avg), ptr(exp_avg_sq), ptr(param_bf16), param.numel(),
+                                    float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                                    ptr(grad_coef), stream_handle()))

@@ -72,7 +72,9 @@ class Predictor:
         return c, m
 
     def predict(self, score_model, noisy_samples, timesteps, encoder_hidden_states, prompt_attention_mask, cfg=None,
-                steps=1, return_double=False, timestep_cond=None):
+                steps=1, return_double=False, timestep_cond=None, return_uncond=False):
+        """predictor.py:30-74.  `return_uncond` (extension, default off) appends the unconditional x0 estimate to
+        the `return_double` tuple: the quantity main.py:508 names `sd_latents_uncond`."""
         pred_type = self.noise_scheduler.config.prediction_type
         for _ in range(steps):
             out_c = score_model(noisy_samples, timestep=timesteps, added_cond_kwargs=self.added_cond_kwargs,
@@ -89,6 +91,10 @@ class Predictor:
                                                        self.sigma_schedule, 1.0, pred_type)      # predictor.py:50-56
                 timesteps = timesteps - timesteps // steps
                 if return_double:
+                    if return_uncond:
+                        _, pred_latents_uncond = _step(out_u, None, noisy_samples, t_long, self.alpha_schedule,
+                                                       self.sigma_schedule, 1.0, pred_type)
+                        return score_pred_cfg, pred_latents, pred_latents_nocfg, pred_latents_uncond
                     return score_pred_cfg, pred_latents, pred_latents_nocfg
                 if steps > 1:  # with steps == 1 the re-noised sample is never used
                     noisy_samples = self.noise_scheduler.add_noise(pred_latents.detach(), score_pred_cfg.detach(),

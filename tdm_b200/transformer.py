@@ -66,7 +66,7 @@ class _Saved:
 
 
 class Transformer2DModel(nn.Module):
-    def __init__(self, config=None, device="cuda", seed=None, **overrides):
+    def __init__(self, config=None, device="cuda", seed=None, init_weights=True, **overrides):
         super().__init__()
         cfg = dict(DEFAULT_CONFIG)
         cfg.update(config or {})
@@ -134,7 +134,8 @@ class Transformer2DModel(nn.Module):
         self._lflat = self._lflat16 = self._lgrad = None
         self._lflat16_version = -1
         self._bind_params()
-        self._init_weights(seed)
+        if init_weights:
+            self._init_weights(seed)
         grid = self.sample_size // p
         self._pos_embed = _sincos_pos_embed(D, grid, grid, max(self.sample_size // 64, 1), device)
         self._pos_cache = {grid: self._pos_embed}
