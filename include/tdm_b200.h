@@ -97,7 +97,8 @@ typedef struct TdmGemm {
   int64_t ld_out_f32;
   void* out_bf16;
   int64_t ld_out_bf16;
-  int32_t tile_n; /* 0 = choose; else 64/128/256 */
+  int32_t tile_n;  /* 0 = choose; else 64/128/192/256 */
+  int32_t split_k; /* 0 = choose; >1 forces split-K (accumulate-only epilogues: res == out_f32, nothing else) */
 } TdmGemm;
 
 int tdm_gemm_bf16(const TdmGemm* g, void* stream);

@@ -1,6 +1,6 @@
 """ORACLE (test infrastructure, never on the product path): CPU restatement of the reference's own
 solver / schedule / loss glue, function by function.  Each function cites the reference lines it
-follows.  It is pinned (tests/test_oracle_vs_reference.py, run wherever /root/reference exists) against
+follows.  It is pinned (tests/test_oracle_glue.py, run wherever /root/reference exists) against
 the REAL reference functions imported unmodified through oracle/reference_import.py, and against the
 committed golden vectors in tests/golden/ (generated from the real reference by
 tests/golden/make_golden.py).

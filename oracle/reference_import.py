@@ -4,7 +4,7 @@ src/models.py and src/predictor.py, unmodified, from /root/reference.
 They only need torch plus `peft.get_peft_model_state_dict` (imported at utils.py:18 and used only by
 the kohya export helper), so a 2-line stub `peft` module is placed in sys.modules for the import.
 /root/reference does not exist on the GPU box: callers must check `available()` and the GPU tests /
-smoke / bench never call this.  Used by tests/test_oracle_vs_reference.py and
+smoke / bench never call this.  Used by tests/test_oracle_glue.py and
 tests/golden/make_golden.py (which writes the committed golden vectors).
 """
 from __future__ import annotations

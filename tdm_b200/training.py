@@ -102,6 +102,7 @@ class FlatAdamW:
         for (p, g, p16), (m, v) in zip(self.groups, self.state):
             ops.adamw_step(p, g, m, v, p16, lr if lr is not None else self.lr, self.betas[0], self.betas[1], self.eps,
                            self.wd, self.t, self._coef)
+        self.model.mark_updated()
 
     def zero_grad(self):
         for _, g, _ in self.groups:

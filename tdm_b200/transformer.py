@@ -143,6 +143,12 @@ class Transformer2DModel(nn.Module):
         self._block_structs = None
         self._scratch = None
         self._infer_ws = None
+        # no-grad forwards of a LoRA model read W_eff = W + (alpha/r) B A, merged once per optimizer step
+        self.lora_merge_infer = True
+        self._flat16_eff = None
+        self._eff_key = None
+        self._merged_structs = None
+        self._update_count = 0
 
     # ------------------------------------------------------------------ parameters
     def _set_param(self, name, tensor, requires_grad=True):
@@ -199,6 +205,7 @@ class Transformer2DModel(nn.Module):
             self._pos_cache = {}
             self._anchor = torch.zeros((), device=new.device, requires_grad=True)
             self._flat16 = self._grad = self._lflat16 = self._lgrad = None
+            self._flat16_eff = self._eff_key = self._merged_structs = None
             self._flat16_version = self._lflat16_version = -1
             self._scratch = self._infer_ws = None
             self._bind_params()
@@ -290,6 +297,7 @@ class Transformer2DModel(nn.Module):
             if ".lora_" in n:
                 p.requires_grad_(True)
         self._lflat16 = self._lgrad = None
+        self._flat16_eff = self._eff_key = self._merged_structs = None
         return self
 
     def lora_parameters(self):
@@ -413,10 +421,50 @@ class Transformer2DModel(nn.Module):
             gs.append(g)
         self._block_structs = (ws, gs)
 
-    def _shape(self, B, N, L):
+    def mark_updated(self):
+        """Called by optimizers that write the arenas through raw pointers (torch's version counters do not see
+        those writes): invalidates the merged LoRA weights."""
+        self._update_count += 1
+
+    def _refresh_merged(self):
+        """W_eff16 = bf16(W32 + (alpha/r) * B A) for every adapted linear: one small tcgen05 GEMM each (K = r),
+        the fp32 master weight as the residual operand.  Redone only after the adapters changed."""
+        key = (self._lflat._version, self._flat._version, self._update_count)
+        if self._flat16_eff is not None and self._eff_key == key:
+            return
+        self._sync_bf16()
+        if self._flat16_eff is None:
+            self._flat16_eff = torch.empty_like(self._flat16)
+            self._merged_structs = None
+        self._flat16_eff.copy_(self._flat16)
+        LA = self._lora_arena
+        for i in range(self.depth):
+            b = f"transformer_blocks.{i}."
+            for t in self.lora_targets:
+                an, bn = b + t + ".lora_A.default.weight", b + t + ".lora_B.default.weight"
+                w32 = self._arena.view(self._flat, b + t + ".weight")
+                weff = self._arena.view(self._flat16_eff, b + t + ".weight")
+                ops.gemm(LA.view(self._lflat16, bn), LA.view(self._lflat16, an), b_mn_major=True, alpha=self.lora_scale,
+                         res=w32, out_bf16=weff)
+        self._eff_key = key
+        if self._merged_structs is None:
+            ws = []
+            for i in range(self.depth):
+                b = f"transformer_blocks.{i}."
+                w = _lib.TdmBlockWeights()
+                w.table = ptr(self._w32(b + "scale_shift_table"))
+                for field, wname in (("qkv", "attn1.to_q"), ("o", "attn1.to_out.0"), ("q2", "attn2.to_q"),
+                                     ("kv2", "attn2.to_k"), ("o2", "attn2.to_out.0"), ("ff1", "ff.net.0.proj"),
+                                     ("ff2", "ff.net.2")):
+                    setattr(w, "w_" + field, ptr(self._arena.view(self._flat16_eff, b + wname + ".weight")))
+                    setattr(w, "b_" + field, ptr(self._w32(b + wname + ".bias")))
+                ws.append(w)
+            self._merged_structs = ws
+
+    def _shape(self, B, N, L, lora=True):
         s = _lib.TdmDitShape()
         s.B, s.N, s.D, s.H, s.L, s.Dff = B, N, self.D, self.H, L, self.Dff
-        s.lora_r = self.lora_r if self._lflat is not None else 0
+        s.lora_r = self.lora_r if (self._lflat is not None and lora) else 0
         s.lora_scale = self.lora_scale
         s.eps = self.eps
         s.train_base = int(self.train_base)
@@ -447,6 +495,10 @@ class Transformer2DModel(nn.Module):
         if self._block_structs is None:
             self._build_block_structs()
         bw, _ = self._block_structs
+        merged = (not save) and self._lflat is not None and self.lora_merge_infer
+        if merged:
+            self._refresh_merged()
+            bw = self._merged_structs
         f32 = dict(device=dev, dtype=torch.float32)
         b16 = dict(device=dev, dtype=torch.bfloat16)
 
@@ -488,7 +540,7 @@ class Transformer2DModel(nn.Module):
         else:
             ctx_bias = None
         # 28 blocks, one C call each
-        s = self._shape(B, N, L)
+        s = self._shape(B, N, L, lora=not merged)
         ws_bytes = lib.tdm_dit_block_ws_bytes(C.byref(s), int(save))
         xs = [x]
         wss = []

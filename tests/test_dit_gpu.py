@@ -81,6 +81,34 @@ def test_forward_per_block_and_output(cfg, B, L):
     assert torch.equal(out2, out)
 
 
+def test_lora_merged_inference_matches_oracle_and_folded_path():
+    """no-grad forwards of a LoRA model read W_eff = W + (alpha/r) B A (merged once per optimizer step); the
+    activations-kept forward folds x A^T B^T into the GEMM K loop.  Both must match the fp32 oracle."""
+    cfg = TINY
+    ref, ours = _pair(cfg, lora=True)
+    lat, t, ctx, mask = _inputs(cfg, 2, 24)
+    with torch.no_grad():
+        out_ref = ref(lat, timestep=t, encoder_hidden_states=ctx, encoder_attention_mask=mask)[0]
+        args = (lat.cuda(), t.cuda(), ctx.cuda(), mask.cuda())
+        out_merged, _ = ours._forward_impl(*args, False)
+        out_folded, _ = ours._forward_impl(*args, True)
+        assert ours._flat16_eff is not None
+        ours.lora_merge_infer = False
+        out_folded_infer, _ = ours._forward_impl(*args, False)
+    assert _rel(out_merged, out_ref) < 2e-2 and _rel(out_folded, out_ref) < 2e-2
+    assert _rel(out_merged, out_folded) < 2e-2
+    assert torch.equal(out_folded_infer, out_folded)
+    # adapters change -> merged weights follow
+    ours.lora_merge_infer = True
+    with torch.no_grad():
+        for n, p in ours.named_parameters():
+            if ".lora_B." in n:
+                p.mul_(-1.0)
+        out2, _ = ours._forward_impl(*args, False)
+        out2f, _ = ours._forward_impl(*args, True)
+    assert _rel(out2, out2f) < 2e-2 and _rel(out2, out_merged) > 1e-3
+
+
 def _grad_check(cfg, B, L, lora, tol):
     ref, ours = _pair(cfg, lora=lora)
     lat, t, ctx, mask = _inputs(cfg, B, L, seed=3)

@@ -18,7 +18,7 @@ def _close(got, ref, tol, what=""):
     assert err / den <= tol, f"{what}: max abs err {err:.4g} / max ref {den:.4g} = {err/den:.3g} > {tol}"
 
 
-@pytest.mark.parametrize("tile_n", [64, 128, 256])
+@pytest.mark.parametrize("tile_n", [64, 128, 192, 256])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
 def test_gemm_majors(tile_n, a_mn, b_mn):
     from tdm_b200 import ops
@@ -108,6 +108,40 @@ def test_gemm_lora_pair_and_segments():
     ops.gemm(x, w[:D], a2=t2, b2=b2, out_f32=out2)
     torch.cuda.synchronize()
     _close(out2, x.float() @ w[:D].float().t() + t2.float() @ b2.float().t(), 2e-4, "rank-16 pair")
+
+
+@pytest.mark.parametrize("split_k", [0, 3, 7])
+def test_gemm_split_k_accumulate(split_k):
+    """wgrad-shaped contraction (few output tiles, long K): split-K partial sums are red.add'ed into out_f32."""
+    from tdm_b200 import ops, _lib
+    tokens, n_out, k_in = 4096, 192, 320
+    dy = _mk((tokens, n_out), seed=20)
+    x = _mk((tokens, k_in), seed=21)
+    acc = torch.randn(n_out, k_in, device="cuda")
+    ref = acc + dy.float().t() @ x.float()
+    ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, res=acc, out_f32=acc, split_k=split_k)
+    torch.cuda.synchronize()
+    _close(acc, ref, 3e-4, f"split_k={split_k}")
+    with pytest.raises(_lib.TdmError):  # split-K is only defined for pure accumulation
+        ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, out_f32=torch.empty_like(acc), split_k=2)
+
+
+def test_gemm_all_activations_match_torch():
+    from tdm_b200 import ops
+    M, N, K = 256, 192, 128
+    a, w = _mk((M, K), seed=30), _mk((N, K), 0.2, seed=31)
+    u = _mk((M, N), seed=32)
+    v = a.float() @ w.float().t()
+    F = torch.nn.functional
+    uf = u.float()
+    sg = torch.sigmoid(uf)
+    cases = {ops.ACT_GELU_TANH: F.gelu(v, approximate="tanh"), ops.ACT_SILU: F.silu(v),
+             ops.ACT_SILU_BWD: v * (sg * (1 + uf * (1 - sg)))}
+    for act, ref in cases.items():
+        out = torch.empty(M, N, device="cuda")
+        ops.gemm(a, w, act=act, act_in=u if act == ops.ACT_SILU_BWD else None, out_f32=out)
+        torch.cuda.synchronize()
+        _close(out, ref, 2e-3, f"act {act}")  # tanh.approx / __expf: ~1e-3 relative
 
 
 def test_gemm_rejects_bad_args():
