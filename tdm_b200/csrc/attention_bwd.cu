@@ -51,7 +51,7 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
 }
 
 __global__ void __launch_bounds__(192, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -251,6 +251,263 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined backward for head_dim <= 80 (PixArt: 72).  Same math as above, but
+//   * dQ has its own TMEM columns and is drained by a SECOND warpgroup with 16-byte vector reds, so the drain
+//     overlaps the next query tile;
+//   * Q / dO tiles are double-buffered in shared memory and the TMA producer runs one tile ahead;
+//   * P^T (bf16) is written back into the S^T columns and feeds dV += P^T dO straight from tensor memory;
+//   * dP^T of the next tile is issued as soon as the compute warps have pulled the current S^T / dP^T into
+//     registers, S^T of the next tile right after dV (tcgen05.mma executes in issue order).
+// TMEM: S^T/P^T [0,128)  dP^T [128,256)  dV [256,336)  dK [336,416)  dQ [416,496).
+// warps 0-3: P / dS (thread == key row)   warps 4-7: dQ drain (thread == query row)   warp 8: TMA   warp 9: MMA
+// ------------------------------------------------------------------------------------------------
+constexpr int BWD_THREADS = 320;
+
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SW128 tiles need 1024-byte alignment
+  const int tile_bytes = p.nd * CHUNK;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + tile_bytes;
+  uint8_t* sQ = sV + tile_bytes;          // 2 stages
+  uint8_t* sdO = sQ + 2 * tile_bytes;     // 2 stages
+  uint8_t* sdSt = sdO + 2 * tile_bytes;   // [128 keys x 128 queries] bf16, 2 chunks
+  float* sLse = reinterpret_cast<float*>(sdSt + 2 * CHUNK);  // 2 x 128 (log2 units)
+  float* sDelta = sLse + 256;                                 // 2 x 128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* kv_full = bars;        // 1
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;   // S^T and dP^T of tile i complete
+  uint64_t* s_free = bars + 6;     // 128: compute warps hold S^T/dP^T of tile i in registers
+  uint64_t* pds_full = bars + 7;   // 128: P^T (TMEM) and dS^T (smem) of tile i written
+  uint64_t* dq_full = bars + 8;    // all MMAs of tile i complete (dQ ready, dS^T smem / Q / dO free)
+  uint64_t* dq_free = bars + 9;    // 128: dQ of tile i drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (p.Sq + 127) / 128;
+  const int dpad = p.dk16 * 16;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(sdp_full, 1);
+    mbar_init(s_free, 128);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_free, 128);
+    fence_barrier_init();
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 336,
+                 tm_dQ = tmem_base + 416;
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmdO);
+      mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
+      for (int c = 0; c < p.nd; ++c) {
+        tma_load_4d(sK + c * CHUNK, &tmK, kv_full, c * 64, k0, h, b);
+        tma_load_4d(sV + c * CHUNK, &tmV, kv_full, c * 64, k0, h, b);
+      }
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&qdo_full[st], 2 * tile_bytes);
+        for (int c = 0; c < p.nd; ++c) {
+          tma_load_4d(sQ + st * tile_bytes + c * CHUNK, &tmQ, &qdo_full[st], c * 64, i * 128, h, b);
+          tma_load_4d(sdO + st * tile_bytes + c * CHUNK, &tmdO, &qdo_full[st], c * 64, i * 128, h, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);    // S^T, dP^T : A K-major, B K-major
+      const uint32_t id_kmn = make_idesc_bf16(128, dpad, 0, 1);  // dV, dK    : A K-major (TMEM / smem), B MN-major
+      const uint32_t id_mnmn = make_idesc_bf16(128, dpad, 1, 1); // dQ        : A MN-major, B MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), adSt = smem_u32(sdSt);
+      auto issue_st = [&](int i) {
+        const uint32_t aQ = smem_u32(sQ + (i & 1) * tile_bytes);
+        for (int k = 0; k < p.dk16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_St, make_sdesc_sw128(aK + off, 16, 1024), make_sdesc_sw128(aQ + off, 16, 1024), id_kk, k != 0);
+        }
+      };
+      auto issue_dpt = [&](int i) {
+        const uint32_t adO = smem_u32(sdO + (i & 1) * tile_bytes);
+        for (int k = 0; k < p.dk16; ++k) {
+          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_dPt, make_sdesc_sw128(aV + off, 16, 1024), make_sdesc_sw128(adO + off, 16, 1024), id_kk, k != 0);
+        }
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      issue_st(0);
+      issue_dpt(0);
+      umma_commit(sdp_full);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        const uint32_t aQ = smem_u32(sQ + st * tile_bytes), adO = smem_u32(sdO + st * tile_bytes);
+        if (i + 1 < n_q) {
+          mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+          mbar_wait(s_free, i & 1);  // the dP^T columns are in registers now
+          tc_fence_after();
+          issue_dpt(i + 1);
+        }
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV += P^T dO : contraction over the 128 queries, A from tensor memory
+          umma_bf16_ts(tm_dV, tm_St + k * 8, make_sdesc_sw128(adO + k * 2048, CHUNK, 1024), id_kmn, (i | k) != 0);
+        if (i + 1 < n_q) {
+          issue_st(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
+          umma_commit(sdp_full);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // dK += dS^T Q
+          const uint32_t offA = (k >> 2) * CHUNK + (k & 3) * 32;
+          umma_bf16(tm_dK, make_sdesc_sw128(adSt + offA, 16, 1024), make_sdesc_sw128(aQ + k * 2048, CHUNK, 1024), id_kmn,
+                    (i | k) != 0);
+        }
+        if (i > 0) {
+          mbar_wait(dq_free, (i - 1) & 1);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ = dS K : contraction over the 128 keys; A = dS^T read MN-major
+          umma_bf16(tm_dQ, make_sdesc_sw128(adSt + k * 2048, CHUNK, 1024), make_sdesc_sw128(aK + k * 2048, CHUNK, 1024),
+                    id_mnmn, k != 0);
+        umma_commit(dq_full);
+        umma_commit(&qdo_empty[st]);
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== P / dS compute (128 threads, thread == key row) =====================
+    const int tid = threadIdx.x;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const float LOG2E = 1.4426950408889634f;
+    const int kv = k0 + tid;
+    float bias_l2 = 0.f;
+    if (kv >= p.Sk) bias_l2 = -INFINITY;
+    else if (p.bias) bias_l2 = p.bias[(long)b * p.Sk + kv] * LOG2E;
+    const long bh = (long)b * p.H + h;
+    uint8_t* drow = sdSt + tid * 128;
+    for (int i = 0; i < n_q; ++i) {
+      const int q = i * 128 + tid;
+      float* lse_s = sLse + (i & 1) * 128;
+      float* del_s = sDelta + (i & 1) * 128;
+      lse_s[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
+      del_s[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tm_St + lane_off + c * 32, rs);
+        tmem_ld32(tm_dPt + lane_off + c * 32, rp);
+        tmem_ld_wait();
+        if (c == 3) {  // everything of this tile is in registers: dP^T may be overwritten
+          tc_fence_before();
+          mbar_arrive(s_free);
+        }
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int x = c * 32 + 2 * j;
+          const float p0 = ex2_fast(fmaf(__uint_as_float(rs[2 * j]), p.scale_log2, bias_l2) - lse_s[x]);
+          const float p1 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2, bias_l2) - lse_s[x + 1]);
+          pk[j] = pack_bf16(p0, p1);
+          dk[j] = pack_bf16(p0 * (__uint_as_float(rp[2 * j]) - del_s[x]), p1 * (__uint_as_float(rp[2 * j + 1]) - del_s[x + 1]));
+        }
+        tmem_st16(tm_St + lane_off + c * 16, pk);  // P^T packed: never passes the S^T columns already consumed
+        if (c == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) {
+          const int U = c * 4 + u4;
+          const int off = (U >> 3) * CHUNK + (((U & 7) ^ (tid & 7)) << 4);
+          *reinterpret_cast<uint4*>(drow + off) = make_uint4(dk[u4 * 4], dk[u4 * 4 + 1], dk[u4 * 4 + 2], dk[u4 * 4 + 3]);
+        }
+      }
+      tmem_st_wait();
+      fence_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    // epilogue: dV, dK of this key tile (thread == key row)
+    mbar_wait(dq_full, (n_q - 1) & 1);
+    tc_fence_after();
+    bf16* dv_row = p.dV + (long)b * p.dv_stride_b + (long)kv * p.dv_stride_s + (long)h * p.dv_stride_h;
+    bf16* dk_row = p.dK + (long)b * p.dk_stride_b + (long)kv * p.dk_stride_s + (long)h * p.dk_stride_h;
+    for (int c = 0; c < p.d; c += 8) {
+      uint32_t rv[8], rk[8];
+      tmem_ld8(tm_dV + lane_off + c, rv);
+      tmem_ld8(tm_dK + lane_off + c, rk);
+      tmem_ld_wait();
+      if (kv < p.Sk) {
+        uint4 w;
+        w.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
+        w.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+        w.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
+        w.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+        *reinterpret_cast<uint4*>(dv_row + c) = w;
+        w.x = pack_bf16(__uint_as_float(rk[0]) * p.scale, __uint_as_float(rk[1]) * p.scale);
+        w.y = pack_bf16(__uint_as_float(rk[2]) * p.scale, __uint_as_float(rk[3]) * p.scale);
+        w.z = pack_bf16(__uint_as_float(rk[4]) * p.scale, __uint_as_float(rk[5]) * p.scale);
+        w.w = pack_bf16(__uint_as_float(rk[6]) * p.scale, __uint_as_float(rk[7]) * p.scale);
+        *reinterpret_cast<uint4*>(dk_row + c) = w;
+      }
+    }
+  } else {
+    // ===================== dQ drain (128 threads, thread == query row) =====================
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    for (int i = 0; i < n_q; ++i) {
+      const int q = i * 128 + tid;
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      float* dq_row = p.dq_accum + (((long)b * p.Sq + q) * p.H + h) * p.d;
+      for (int c = 0; c < p.d; c += 8) {
+        uint32_t r[8];
+        tmem_ld8(tm_dQ + lane_off + c, r);
+        tmem_ld_wait();
+        if (q < p.Sq) {
+          red_add_v4(dq_row + c, __uint_as_float(r[0]) * p.scale, __uint_as_float(r[1]) * p.scale,
+                     __uint_as_float(r[2]) * p.scale, __uint_as_float(r[3]) * p.scale);
+          red_add_v4(dq_row + c + 4, __uint_as_float(r[4]) * p.scale, __uint_as_float(r[5]) * p.scale,
+                     __uint_as_float(r[6]) * p.scale, __uint_as_float(r[7]) * p.scale);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_free);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // fp32 [rows, cols] (ld_in) -> bf16 [rows, cols] (ld_out): dQ scratch -> its slot in the d(qkv) matrix
 __global__ void cast2d_f32_bf16_kernel(const float* in, long ld_in, bf16* out, long ld_out, int rows, int cols) {
   const int c4 = cols / 4;
@@ -298,14 +555,24 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   p.bias = a->bias; p.lse = a->lse; p.delta = a->delta; p.dq_accum = a->dq_accum;
   p.dK = (bf16*)a->dK; p.dk_stride_b = a->dk_stride_b; p.dk_stride_s = a->dk_stride_s; p.dk_stride_h = a->dk_stride_h;
   p.dV = (bf16*)a->dV; p.dv_stride_b = a->dv_stride_b; p.dv_stride_s = a->dv_stride_s; p.dv_stride_h = a->dv_stride_h;
-  const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
-  }
   dim3 grid((a->Sk + 127) / 128, a->H, a->B);
-  ::tdm::count_launch(); attn_bwd_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+  if (p.dk16 * 16 <= 80 && (((long)a->H * a->d) % 4 == 0) && (a->d % 4 == 0)) {
+    const int smem = 6 * p.nd * CHUNK + 2 * CHUNK + 2048 + 256;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      smem_set = smem;
+    }
+    ::tdm::count_launch(); attn_bwd_kernel<<<grid, BWD_THREADS, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+  } else {
+    const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
+    static int smem_set_w = 0;
+    if (smem > smem_set_w) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      smem_set_w = smem;
+    }
+    ::tdm::count_launch(); attn_bwd_wide_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+  }
   TDM_CHECK_CUDA(cudaGetLastError());
   // dQ scratch [B*Sq, H*d] fp32 -> bf16 dQ with the caller's strides (requires the [tokens, H*d] layout)
   const int nblk = num_sms() * 8;

@@ -36,6 +36,9 @@ __device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
   tmem_st8(taddr, r);
 }
 
+// TMEM map: S ping-pong at columns [0,128) and [128,256); O at [256, 256+pad16(d)).  P(j) (bf16, two keys per
+// 32-bit column) overwrites columns [0,64) of the S buffer it was computed from and is the A operand of the
+// P V contraction directly from tensor memory: P never touches shared memory.
 __global__ void __launch_bounds__(192, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -45,8 +48,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + tile_bytes;           // 2 stages
   uint8_t* sV = sK + 2 * tile_bytes;       // 2 stages
-  uint8_t* sP = sV + 2 * tile_bytes;       // [128 x 128] bf16 = 2 chunks
-  float* sBias = reinterpret_cast<float*>(sP + 2 * CHUNK_BYTES);  // 2 x 128 floats
+  float* sBias = reinterpret_cast<float*>(sV + 2 * tile_bytes);  // 2 x 128 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
@@ -79,7 +81,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
-  const uint32_t tmem_O = tmem_base + 256;  // 128 columns
+  const uint32_t tmem_O = tmem_base + 256;  // <= 128 columns
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -104,8 +106,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
-      const uint32_t idesc_pv = make_idesc_bf16(128, p.nd * 64, 0, 1);  // B = V is MN-major (d contiguous)
-      const uint32_t q_base = smem_u32(sQ), p_base = smem_u32(sP);
+      const uint32_t idesc_pv = make_idesc_bf16(128, p.dk16 * 16, 0, 1);  // A = P from TMEM; B = V MN-major (d contiguous)
+      const uint32_t q_base = smem_u32(sQ);
       auto issue_qk = [&](int j) {
         const int st = j & 1;
         mbar_wait(&k_full[st], (j >> 1) & 1);
@@ -121,95 +123,107 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < n_kv; ++j) {
+        // S((j+1)&1) still holds P(j-1): tcgen05.mma executes in issue order, so this S^T write follows P V (j-1)
         if (j + 1 < n_kv) issue_qk(j + 1);
         const int st = j & 1;
         mbar_wait(p_full, j & 1);
         mbar_wait(&v_full[st], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t v_base = smem_u32(sV + st * tile_bytes);
+        const uint32_t p_addr = tmem_S + (j & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {
-          const uint64_t da = make_sdesc_sw128(p_base + (k >> 2) * CHUNK_BYTES + (k & 3) * 32, 16, 1024);
+        for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed TMEM columns per step
           const uint64_t db = make_sdesc_sw128(v_base + k * 2048, CHUNK_BYTES, 1024);
-          umma_bf16(tmem_O, da, db, idesc_pv, (j | k) != 0);
+          umma_bf16_ts(tmem_O, p_addr + k * 8, db, idesc_pv, (j | k) != 0);
         }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
       }
     }
   } else {
-    // ===================== softmax / correction / epilogue (128 threads) =====================
-    const int tid = threadIdx.x;  // query row within the tile, TMEM lane
+    // ===================== softmax / correction / epilogue (128 threads, thread == query row) =====================
+    const int tid = threadIdx.x;
     const uint32_t lane_off = uint32_t(warp * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_used = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int buf = j & 1;
-      {  // additive bias (pre-multiplied by log2 e) and the key-padding mask for this tile
+      const bool need_bias = p.bias != nullptr || (j + 1) * ATT_BN > p.Sk;  // CTA-uniform
+      if (need_bias) {  // additive key bias (pre-multiplied by log2 e) and the key-padding mask of a ragged last tile
         const int kv = j * ATT_BN + tid;
         float bv = 0.f;
         if (kv >= p.Sk) bv = -INFINITY;
         else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
         sBias[buf * 128 + tid] = bv;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float* bias_s = sBias + buf * 128;
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
+      uint32_t sr[128];
+      tmem_ld32(s_addr, sr);
+      tmem_ld32(s_addr + 32, sr + 32);
+      tmem_ld32(s_addr + 64, sr + 64);
+      tmem_ld32(s_addr + 96, sr + 96);
+      tmem_ld_wait();
       float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + c * 32, r);
-        tmem_ld_wait();
+      if (need_bias) {
+        const float* bias_s = sBias + buf * 128;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaf(__uint_as_float(r[i]), p.scale_log2, bias_s[c * 32 + i]));
+        for (int i = 0; i < 128; ++i) {
+          const float v = fmaf(__uint_as_float(sr[i]), p.scale_log2, bias_s[i]);
+          sr[i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+        mx *= p.scale_log2;  // scale > 0
       }
-      const float m_new = fmaxf(m_run, mx);
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);  // O and the P buffer are free again
+      // Lazy rescale: O and l keep the stale maximum until it is exceeded by more than 2^8 (exact after the final
+      // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform because tcgen05.ld/st are collective.
+      const float m_new = fmaxf(m_used, mx);
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, m_new - m_used > 8.f)) {
+        mbar_wait(pv_done, (j - 1) & 1);  // O must not be rescaled under an in-flight P V
         tc_fence_after();
-        const float alpha = exp2f(m_run - m_new);
+        const float alpha = ex2_fast(m_used - m_new);
         l_run *= alpha;
-        if (__any_sync(0xffffffffu, alpha != 1.f)) {  // tcgen05.ld/st are warp-collective
-          for (int c = 0; c < p.d; c += 8) {
-            uint32_t r[8];
-            tmem_ld8(tmem_O + lane_off + c, r);
-            tmem_ld_wait();
-            float v[8];
+        m_used = m_new;
+        for (int c = 0; c < p.d; c += 8) {
+          uint32_t r[8];
+          tmem_ld8(tmem_O + lane_off + c, r);
+          tmem_ld_wait();
+          float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-            tmem_st8w(tmem_O + lane_off + c, v);
-          }
-          tmem_st_wait();
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+          tmem_st8w(tmem_O + lane_off + c, v);
+        }
+        tmem_st_wait();
+      }
+      // P is packed in place: sr[i] <- bf16x2(p[2i], p[2i+1]) (the write index never passes the read index)
+      if (need_bias) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float p0 = ex2_fast(__uint_as_float(sr[2 * i]) - m_used);
+          const float p1 = ex2_fast(__uint_as_float(sr[2 * i + 1]) - m_used);
+          l_run += p0 + p1;
+          sr[i] = pack_bf16(p0, p1);
+        }
+      } else {
+        const float nm = -m_used;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
+          const float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
+          l_run += p0 + p1;
+          sr[i] = pack_bf16(p0, p1);
         }
       }
-      m_run = m_new;
-      uint8_t* prow = sP + tid * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(s_addr + c * 32, r);
-        tmem_ld_wait();
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          pv[i] = exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2, bias_s[c * 32 + i]) - m_new);
-          l_run += pv[i];
-        }
-#pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          const int U = c * 4 + u4;  // 16-byte unit index within the 128-key row
-          uint4 w;
-          w.x = pack_bf16(pv[u4 * 8 + 0], pv[u4 * 8 + 1]);
-          w.y = pack_bf16(pv[u4 * 8 + 2], pv[u4 * 8 + 3]);
-          w.z = pack_bf16(pv[u4 * 8 + 4], pv[u4 * 8 + 5]);
-          w.w = pack_bf16(pv[u4 * 8 + 6], pv[u4 * 8 + 7]);
-          *reinterpret_cast<uint4*>(prow + (U >> 3) * CHUNK_BYTES + (((U & 7) ^ (tid & 7)) << 4)) = w;
-        }
-      }
-      fence_async_smem();
+      tmem_st32(s_addr, sr);
+      tmem_st32(s_addr + 32, sr + 32);
+      tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
     }
@@ -218,7 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q = q0 + tid;
     const float inv_l = 1.f / l_run;
     if (q < p.Sq) {
-      if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+      if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_used + log2f(l_run)) * 0.6931471805599453f;
     }
     bf16* orow = p.O + (long)b * p.o_stride_b + (long)q * p.o_stride_s + (long)h * p.o_stride_h;
     for (int c = 0; c < p.d; c += 8) {
@@ -278,7 +292,7 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   p.bias = a->bias;
   p.O = (bf16*)a->O; p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.lse = a->lse;
-  const int smem = 5 * p.nd * CHUNK_BYTES + 2 * CHUNK_BYTES + 1024 + 256 + 1024;
+  const int smem = 5 * p.nd * CHUNK_BYTES + 1024 + 256 + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
     TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -56,8 +56,9 @@ struct GemmCfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int STAGING_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int STAGING_BYTES = 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
 };
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
@@ -204,13 +205,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // TMEM -> registers (thread == accumulator row) -> shared-memory transpose -> lanes own COLUMNS:
-    // every global access below is a contiguous row segment (128 B of fp32 / 64 B of bf16 per half warp).
+    // thread == accumulator row (tcgen05.ld 32x32b): all 32 values of a chunk sit in registers, so the fused math
+    // has 32-way ILP and every global access is a 16-byte vector; each thread touches whole 32-byte sectors.
     const int ew = warp - 4;
     const int q = ew & 3;    // == warp % 4: the TMEM lane quarter this warp may read
-    const int ch = ew >> 2;  // even or odd 32-column chunks
-    float* stg = staging + ew * (32 * EPI_PITCH);
-    const int half = lane >> 4, l16 = lane & 15;
+    const int ch = ew >> 2;  // even / odd 32-column chunks of the tile
     int it = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const int tile = unit / p.splits;
@@ -218,82 +217,100 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / p.num_n_tiles) * BM;
       const int n0 = (tile % p.num_n_tiles) * BN;
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
-      const float* gate_tile =
-          (p.gate && p.gate_uniform) ? p.gate + (long)(m0 / p.rows_per_gate) * p.gate_stride : nullptr;
+      const float* gate_row = nullptr;
+      if (p.gate && row_ok) gate_row = p.gate + (long)(m / p.rows_per_gate) * p.gate_stride;
+      const long rr = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
 #pragma unroll 1
       for (int c = ch * 32; c < BN; c += 64) {
         if (n0 + c >= p.N) break;  // warp-uniform
-        {
-          uint32_t acc[32];
-          tmem_ld32(taddr + c, acc);
-          tmem_ld_wait();
-          float4* dst = reinterpret_cast<float4*>(stg + lane * EPI_PITCH);
+        uint32_t acc[32];
+        tmem_ld32(taddr + c, acc);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
+          float* o = p.out_f32 + (long)m * p.ld_out_f32 + n0 + c;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            dst[j] = make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]),
-                                 __uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]));
+          for (int i = 0; i < 32; ++i)
+            if (n0 + c + i < p.N) atomicAdd(o + i, p.alpha * __uint_as_float(acc[i]));
+          continue;
         }
-        __syncwarp();
-        const int n = n0 + c + 2 * l16;  // this lane's two columns
-        const bool col_ok = n < p.N;     // N is even, so n + 1 < N as well
-        float2 b2 = make_float2(0.f, 0.f), g2 = make_float2(1.f, 1.f);
-        if (col_ok) {
-          if (p.bias) b2 = *reinterpret_cast<const float2*>(p.bias + n);
-          if (gate_tile) g2 = *reinterpret_cast<const float2*>(gate_tile + n);
-        }
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int r = 2 * i + half;
-          const int m = m0 + q * 32 + r;
-          float2 v = *reinterpret_cast<const float2*>(stg + r * EPI_PITCH + 2 * l16);
-          if (m < p.M && col_ok) {
-            if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
-              atomicAdd(p.out_f32 + (long)m * p.ld_out_f32 + n, p.alpha * v.x);
-              atomicAdd(p.out_f32 + (long)m * p.ld_out_f32 + n + 1, p.alpha * v.y);
-              continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c + g * 8;
+          if (n < p.N) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(acc[g * 8 + i]);
+            if (p.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            v.x = p.alpha * v.x + b2.x;
-            v.y = p.alpha * v.y + b2.y;
-            if (p.pre_out) *reinterpret_cast<uint32_t*>(p.pre_out + (long)m * p.ld_pre + n) = pack_bf16(v.x, v.y);
-            if (p.pre_out_f32) *reinterpret_cast<float2*>(p.pre_out_f32 + (long)m * p.ld_pre_f32 + n) = v;
+            if (p.pre_out) {
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(p.pre_out + (long)m * p.ld_pre + n) = o;
+            }
+            if (p.pre_out_f32) {
+              float* o = p.pre_out_f32 + (long)m * p.ld_pre_f32 + n;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
             if (p.act == TDM_ACT_GELU_TANH) {
-              v.x = gelu_tanh_fast(v.x);
-              v.y = gelu_tanh_fast(v.y);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_fast(v[i]);
             } else if (p.act == TDM_ACT_GELU_TANH_BWD) {
-              const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.act_in + (long)m * p.ld_act + n));
-              v.x *= gelu_tanh_grad_fast(u.x);
-              v.y *= gelu_tanh_grad_fast(u.y);
+              const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+              const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+              v[0] *= gelu_tanh_grad_fast(u0.x); v[1] *= gelu_tanh_grad_fast(u0.y);
+              v[2] *= gelu_tanh_grad_fast(u1.x); v[3] *= gelu_tanh_grad_fast(u1.y);
+              v[4] *= gelu_tanh_grad_fast(u2.x); v[5] *= gelu_tanh_grad_fast(u2.y);
+              v[6] *= gelu_tanh_grad_fast(u3.x); v[7] *= gelu_tanh_grad_fast(u3.y);
             } else if (p.act == TDM_ACT_SILU) {
-              v.x = v.x / (1.f + __expf(-v.x));
-              v.y = v.y / (1.f + __expf(-v.y));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
             } else if (p.act == TDM_ACT_SILU_BWD) {
-              const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(p.act_in + (long)m * p.ld_act + n));
-              const float sx = 1.f / (1.f + __expf(-u.x)), sy = 1.f / (1.f + __expf(-u.y));
-              v.x *= sx * (1.f + u.x * (1.f - sx));
-              v.y *= sy * (1.f + u.y * (1.f - sy));
+              const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+              const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+              const float uu[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float sg = 1.f / (1.f + __expf(-uu[i]));
+                v[i] *= sg * (1.f + uu[i] * (1.f - sg));
+              }
             }
-            if (p.gate) {
-              float2 g = g2;
-              if (!gate_tile)
-                g = *reinterpret_cast<const float2*>(p.gate + (long)(m / p.rows_per_gate) * p.gate_stride + n);
-              v.x *= g.x;
-              v.y *= g.y;
+            if (gate_row) {
+              const float4 g0 = *reinterpret_cast<const float4*>(gate_row + n);
+              const float4 g1 = *reinterpret_cast<const float4*>(gate_row + n + 4);
+              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+              v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
             }
             if (p.res) {
-              const long rr = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
-              const float2 r2 = *reinterpret_cast<const float2*>(p.res + rr * p.ld_res + n);
-              v.x += r2.x;
-              v.y += r2.y;
+              const float4 r0 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n);
+              const float4 r1 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n + 4);
+              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+              v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
             }
-            if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + (long)m * p.ld_out_f32 + n) = v;
-            if (p.out_bf16)
-              *reinterpret_cast<uint32_t*>(p.out_bf16 + (long)m * p.ld_out_bf16 + n) = pack_bf16(v.x, v.y);
+            if (p.out_f32) {
+              float* o = p.out_f32 + (long)m * p.ld_out_f32 + n;
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (p.out_bf16) {
+              uint4 o;
+              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+              *reinterpret_cast<uint4*>(p.out_bf16 + (long)m * p.ld_out_bf16 + n) = o;
+            }
           }
         }
-        __syncwarp();  // the staging rows are rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -439,7 +456,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
       const double mma = double(waves) * 2.0 * double(b);
       return bw > mma ? bw : mma;
     };
-    const int cands[4] = {256, 192, 128, 64};
+    const int cands[4] = {192, 256, 128, 64};  // ties go to 192: measured faster than 256 at N = 1152 / 3456
     double best = 1e30;
     bn = 256;
     for (int i = 0; i < 4; ++i) {

@@ -120,6 +120,9 @@ def _attn_ref(q, k, v, scale, bias):
     (2, 16, 1024, 120, 72, True),    # PixArt cross-attention to 120 T5 tokens with a key mask
     (1, 2, 200, 77, 72, True),       # ragged sizes
     (1, 2, 384, 300, 40, True),
+    (1, 2, 256, 256, 128, False),    # head_dim > 80: the wide backward kernel
+    (1, 3, 130, 250, 96, True),
+    (2, 16, 4096, 4096, 72, False),  # PixArt-1024 sequence length (BASELINE.json configs[4])
 ])
 def test_attention_fwd_bwd(B, H, Sq, Sk, d, cross):
     from tdm_b200 import ops
