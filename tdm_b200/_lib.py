@@ -9,7 +9,9 @@ import ctypes as C
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libtdm_b200.so"
+import os as _os
+
+LIB_PATH = Path(_os.environ["TDM_B200_LIB"]) if _os.environ.get("TDM_B200_LIB") else _HERE / "libtdm_b200.so"
 
 _lib = None
 

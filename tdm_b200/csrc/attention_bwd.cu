@@ -260,9 +260,10 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 //   * dP^T of the next tile is issued as soon as the compute warps have pulled the current S^T / dP^T into
 //     registers, S^T of the next tile right after dV (tcgen05.mma executes in issue order).
 // TMEM: S^T/P^T [0,128)  dP^T [128,256)  dV [256,336)  dK [336,416)  dQ [416,496).
-// warps 0-3: P / dS (thread == key row)   warps 4-7: dQ drain (thread == query row)   warp 8: TMA   warp 9: MMA
+// warps 0-7: P / dS (thread == key row; two halves of the query columns)   warps 8-11: dQ drain (thread == query row)
+// warp 12: TMA   warp 13: MMA
 // ------------------------------------------------------------------------------------------------
-constexpr int BWD_THREADS = 320;
+constexpr int BWD_THREADS = 448;  // 8 compute warps (two halves of the query columns) + 4 drain warps + TMA + MMA
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -302,13 +303,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(pds_full, 128);
+    mbar_init(s_free, 256);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 128);
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc(tmem_slot, 512);
+  if (warp == 13) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -316,7 +317,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 336,
                  tm_dQ = tmem_base + 416;
 
-  if (warp == 8) {
+  if (warp == 12) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
@@ -328,7 +329,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
-        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait_relaxed(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * tile_bytes);
         for (int c = 0; c < p.nd; ++c) {
           tma_load_4d(sQ + st * tile_bytes + c * CHUNK, &tmQ, &qdo_full[st], c * 64, i * 128, h, b);
@@ -336,73 +337,97 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);    // S^T, dP^T : A K-major, B K-major
-      const uint32_t id_kmn = make_idesc_bf16(128, dpad, 0, 1);  // dV, dK    : A K-major (TMEM / smem), B MN-major
-      const uint32_t id_mnmn = make_idesc_bf16(128, dpad, 1, 1); // dQ        : A MN-major, B MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), adSt = smem_u32(sdSt);
-      auto issue_st = [&](int i) {
-        const uint32_t aQ = smem_u32(sQ + (i & 1) * tile_bytes);
-        for (int k = 0; k < p.dk16; ++k) {
-          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
-          umma_bf16(tm_St, make_sdesc_sw128(aK + off, 16, 1024), make_sdesc_sw128(aQ + off, 16, 1024), id_kk, k != 0);
+    // Warp-convergent: every lane polls and computes the (uniform) descriptors, tcgen05 ops under elect.sync only.
+    const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);    // S^T, dP^T : A K-major, B K-major
+    const uint32_t id_kmn = make_idesc_bf16(128, dpad, 0, 1);  // dV, dK    : A K-major (TMEM / smem), B MN-major
+    const uint32_t id_mnmn = make_idesc_bf16(128, dpad, 1, 1); // dQ        : A MN-major, B MN-major
+    const uint64_t dK_k = make_sdesc_sw128(smem_u32(sK), 16, 1024);       // K as K-major operand (S^T)
+    const uint64_t dV_k = make_sdesc_sw128(smem_u32(sV), 16, 1024);       // V as K-major operand (dP^T)
+    const uint64_t dK_mn = make_sdesc_sw128(smem_u32(sK), CHUNK, 1024);   // K as MN-major operand (dQ)
+    const uint64_t dQ_k0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t dQ_mn0 = make_sdesc_sw128(smem_u32(sQ), CHUNK, 1024);
+    const uint64_t ddO_k0 = make_sdesc_sw128(smem_u32(sdO), 16, 1024);
+    const uint64_t ddO_mn0 = make_sdesc_sw128(smem_u32(sdO), CHUNK, 1024);
+    const uint64_t ddS_k = make_sdesc_sw128(smem_u32(sdSt), 16, 1024);
+    const uint64_t ddS_mn = make_sdesc_sw128(smem_u32(sdSt), CHUNK, 1024);
+    const uint32_t stage_step = uint32_t(tile_bytes) >> 4;
+    const int dk16 = p.dk16;
+    auto issue_st = [&](int i) {  // caller holds the election
+      const uint64_t qd = dQ_k0 + uint64_t((i & 1) * stage_step);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < dk16) {
+          const uint32_t off = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
+          umma_bf16(tm_St, dK_k + off, qd + off, id_kk, k != 0);
         }
-      };
-      auto issue_dpt = [&](int i) {
-        const uint32_t adO = smem_u32(sdO + (i & 1) * tile_bytes);
-        for (int k = 0; k < p.dk16; ++k) {
-          const uint32_t off = (k >> 2) * CHUNK + (k & 3) * 32;
-          umma_bf16(tm_dPt, make_sdesc_sw128(aV + off, 16, 1024), make_sdesc_sw128(adO + off, 16, 1024), id_kk, k != 0);
+    };
+    auto issue_dpt = [&](int i) {
+      const uint64_t od = ddO_k0 + uint64_t((i & 1) * stage_step);
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < dk16) {
+          const uint32_t off = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
+          umma_bf16(tm_dPt, dV_k + off, od + off, id_kk, k != 0);
         }
-      };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&qdo_full[0], 0);
-      tc_fence_after();
+    };
+    mbar_wait(kv_full, 0);
+    mbar_wait(&qdo_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
       issue_st(0);
       issue_dpt(0);
       umma_commit(sdp_full);
-      for (int i = 0; i < n_q; ++i) {
-        const int st = i & 1;
-        const uint32_t aQ = smem_u32(sQ + st * tile_bytes), adO = smem_u32(sdO + st * tile_bytes);
-        if (i + 1 < n_q) {
-          mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-          mbar_wait(s_free, i & 1);  // the dP^T columns are in registers now
-          tc_fence_after();
-          issue_dpt(i + 1);
-        }
-        mbar_wait(pds_full, i & 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      if (i + 1 < n_q) {
+        mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
+        mbar_wait(s_free, i & 1);  // the dP^T columns are in registers now
         tc_fence_after();
+        if (elect_one()) issue_dpt(i + 1);
+        __syncwarp();
+      }
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t od_mn = ddO_mn0 + uint64_t(st * stage_step), qd_mn = dQ_mn0 + uint64_t(st * stage_step);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV += P^T dO : contraction over the 128 queries, A from tensor memory
-          umma_bf16_ts(tm_dV, tm_St + k * 8, make_sdesc_sw128(adO + k * 2048, CHUNK, 1024), id_kmn, (i | k) != 0);
+          umma_bf16_ts(tm_dV, tm_St + (k >> 2) * 64 + (k & 3) * 8, od_mn + uint64_t(k * (2048 >> 4)), id_kmn, (i | k) != 0);
         if (i + 1 < n_q) {
           issue_st(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
           umma_commit(sdp_full);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dK += dS^T Q
-          const uint32_t offA = (k >> 2) * CHUNK + (k & 3) * 32;
-          umma_bf16(tm_dK, make_sdesc_sw128(adSt + offA, 16, 1024), make_sdesc_sw128(aQ + k * 2048, CHUNK, 1024), id_kmn,
-                    (i | k) != 0);
+          const uint32_t offA = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
+          umma_bf16(tm_dK, ddS_k + offA, qd_mn + uint64_t(k * (2048 >> 4)), id_kmn, (i | k) != 0);
         }
-        if (i > 0) {
-          mbar_wait(dq_free, (i - 1) & 1);
-          tc_fence_after();
-        }
+      }
+      __syncwarp();
+      if (i > 0) {
+        mbar_wait(dq_free, (i - 1) & 1);
+        tc_fence_after();
+      }
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dQ = dS K : contraction over the 128 keys; A = dS^T read MN-major
-          umma_bf16(tm_dQ, make_sdesc_sw128(adSt + k * 2048, CHUNK, 1024), make_sdesc_sw128(aK + k * 2048, CHUNK, 1024),
-                    id_mnmn, k != 0);
+          umma_bf16(tm_dQ, ddS_mn + uint64_t(k * (2048 >> 4)), dK_mn + uint64_t(k * (2048 >> 4)), id_mnmn, k != 0);
         umma_commit(dq_full);
         umma_commit(&qdo_empty[st]);
       }
+      __syncwarp();
     }
-  } else if (warp < 4) {
-    // ===================== P / dS compute (128 threads, thread == key row) =====================
-    const int tid = threadIdx.x;
-    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  } else if (warp < 8) {
+    // ===================== P / dS compute (2 x 128 threads, thread == key row) =====================
+    // warps 0-3 own query columns [0,64) of every tile, warps 4-7 columns [64,128): two warps per SM sub-partition
+    // hide each other's TMEM / MUFU / shared-memory latencies.
+    const int tid = threadIdx.x & 127;
+    const int wg = threadIdx.x >> 7;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
     const int kv = k0 + tid;
     float bias_l2 = 0.f;
@@ -414,32 +439,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int q = i * 128 + tid;
       float* lse_s = sLse + (i & 1) * 128;
       float* del_s = sDelta + (i & 1) * 128;
-      lse_s[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
-      del_s[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (wg == 0) lse_s[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
+      else del_s[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = wg * 2 + cc;
         uint32_t rs[32], rp[32];
         tmem_ld32(tm_St + lane_off + c * 32, rs);
         tmem_ld32(tm_dPt + lane_off + c * 32, rp);
         tmem_ld_wait();
-        if (c == 3) {  // everything of this tile is in registers: dP^T may be overwritten
+        if (cc == 1) {  // everything this thread needs of the tile is in registers: dP^T may be overwritten
           tc_fence_before();
           mbar_arrive(s_free);
         }
         uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 16; j += 2) {
           const int x = c * 32 + 2 * j;
-          const float p0 = ex2_fast(fmaf(__uint_as_float(rs[2 * j]), p.scale_log2, bias_l2) - lse_s[x]);
-          const float p1 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2, bias_l2) - lse_s[x + 1]);
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + x);
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + x);
+          const float p0 = ex2_fast(fmaf(__uint_as_float(rs[2 * j]), p.scale_log2, bias_l2) - l4.x);
+          const float p1 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2, bias_l2) - l4.y);
+          const float p2 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 2]), p.scale_log2, bias_l2) - l4.z);
+          const float p3 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 3]), p.scale_log2, bias_l2) - l4.w);
           pk[j] = pack_bf16(p0, p1);
-          dk[j] = pack_bf16(p0 * (__uint_as_float(rp[2 * j]) - del_s[x]), p1 * (__uint_as_float(rp[2 * j + 1]) - del_s[x + 1]));
+          pk[j + 1] = pack_bf16(p2, p3);
+          dk[j] = pack_bf16(p0 * (__uint_as_float(rp[2 * j]) - d4.x), p1 * (__uint_as_float(rp[2 * j + 1]) - d4.y));
+          dk[j + 1] = pack_bf16(p2 * (__uint_as_float(rp[2 * j + 2]) - d4.z), p3 * (__uint_as_float(rp[2 * j + 3]) - d4.w));
         }
-        tmem_st16(tm_St + lane_off + c * 16, pk);  // P^T packed: never passes the S^T columns already consumed
-        if (c == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
+        // P^T packed into this warpgroup's OWN half of the S^T columns ([0,32) / [64,96)): never passes the columns
+        // it still has to read, and never touches the other warpgroup's
+        tmem_st16(tm_St + lane_off + wg * 64 + cc * 16, pk);
+        if (cc == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           const int U = c * 4 + u4;
@@ -452,37 +486,33 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       mbar_arrive(pds_full);
     }
-    // epilogue: dV, dK of this key tile (thread == key row)
+    // epilogue: warps 0-3 write dV, warps 4-7 write dK of this key tile (thread == key row)
     mbar_wait(dq_full, (n_q - 1) & 1);
     tc_fence_after();
-    bf16* dv_row = p.dV + (long)b * p.dv_stride_b + (long)kv * p.dv_stride_s + (long)h * p.dv_stride_h;
-    bf16* dk_row = p.dK + (long)b * p.dk_stride_b + (long)kv * p.dk_stride_s + (long)h * p.dk_stride_h;
+    bf16* out_row = wg == 0 ? p.dV + (long)b * p.dv_stride_b + (long)kv * p.dv_stride_s + (long)h * p.dv_stride_h
+                            : p.dK + (long)b * p.dk_stride_b + (long)kv * p.dk_stride_s + (long)h * p.dk_stride_h;
+    const uint32_t tm_src = wg == 0 ? tm_dV : tm_dK;
+    const float osc = wg == 0 ? 1.f : p.scale;
     for (int c = 0; c < p.d; c += 8) {
-      uint32_t rv[8], rk[8];
-      tmem_ld8(tm_dV + lane_off + c, rv);
-      tmem_ld8(tm_dK + lane_off + c, rk);
+      uint32_t r[8];
+      tmem_ld8(tm_src + lane_off + c, r);
       tmem_ld_wait();
       if (kv < p.Sk) {
         uint4 w;
-        w.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
-        w.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
-        w.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
-        w.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
-        *reinterpret_cast<uint4*>(dv_row + c) = w;
-        w.x = pack_bf16(__uint_as_float(rk[0]) * p.scale, __uint_as_float(rk[1]) * p.scale);
-        w.y = pack_bf16(__uint_as_float(rk[2]) * p.scale, __uint_as_float(rk[3]) * p.scale);
-        w.z = pack_bf16(__uint_as_float(rk[4]) * p.scale, __uint_as_float(rk[5]) * p.scale);
-        w.w = pack_bf16(__uint_as_float(rk[6]) * p.scale, __uint_as_float(rk[7]) * p.scale);
-        *reinterpret_cast<uint4*>(dk_row + c) = w;
+        w.x = pack_bf16(__uint_as_float(r[0]) * osc, __uint_as_float(r[1]) * osc);
+        w.y = pack_bf16(__uint_as_float(r[2]) * osc, __uint_as_float(r[3]) * osc);
+        w.z = pack_bf16(__uint_as_float(r[4]) * osc, __uint_as_float(r[5]) * osc);
+        w.w = pack_bf16(__uint_as_float(r[6]) * osc, __uint_as_float(r[7]) * osc);
+        *reinterpret_cast<uint4*>(out_row + c) = w;
       }
     }
   } else {
     // ===================== dQ drain (128 threads, thread == query row) =====================
-    const int tid = threadIdx.x - 128;
+    const int tid = threadIdx.x - 256;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     for (int i = 0; i < n_q; ++i) {
       const int q = i * 128 + tid;
-      mbar_wait(dq_full, i & 1);
+      mbar_wait_relaxed(dq_full, i & 1);
       tc_fence_after();
       float* dq_row = p.dq_accum + (((long)b * p.Sq + q) * p.H + h) * p.d;
       for (int c = 0; c < p.d; c += 8) {
@@ -502,7 +532,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == 13) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

@@ -39,7 +39,12 @@ __device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
 // TMEM map: S ping-pong at columns [0,128) and [128,256); O at [256, 256+pad16(d)).  P(j) (bf16, two keys per
 // 32-bit column) overwrites columns [0,64) of the S buffer it was computed from and is the A operand of the
 // P V contraction directly from tensor memory: P never touches shared memory.
-__global__ void __launch_bounds__(192, 1)
+// Two softmax warpgroups share every 128-query tile: warps 0-3 own keys [0,64) of the tile, warps 4-7 keys
+// [64,128) (thread == query row in both), so each SM sub-partition always has two warps to hide the
+// TMEM / MUFU / shared-memory latencies of the other; they exchange row maxima through shared memory.
+constexpr int FWD_THREADS = 320;  // 8 softmax warps + TMA warp + MMA warp
+
+__global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -49,7 +54,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = sQ + tile_bytes;           // 2 stages
   uint8_t* sV = sK + 2 * tile_bytes;       // 2 stages
   float* sBias = reinterpret_cast<float*>(sV + 2 * tile_bytes);  // 2 x 128 floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 256);
+  float* sMax = sBias + 256;                                      // [2 tiles][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 512);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;    // [2]
   uint64_t* v_full = bars + 3;    // [2]
@@ -71,11 +77,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_full, 128);
+    mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc(tmem_slot, 512);
+  if (warp == 9) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -83,7 +89,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
   const uint32_t tmem_O = tmem_base + 256;  // <= 128 columns
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
@@ -102,86 +108,120 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tma_load_4d(sV + st * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[st], c * 64, j * ATT_BN, h, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
-      const uint32_t idesc_pv = make_idesc_bf16(128, p.dk16 * 16, 0, 1);  // A = P from TMEM; B = V MN-major (d contiguous)
-      const uint32_t q_base = smem_u32(sQ);
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t k_base = smem_u32(sK + st * tile_bytes);
-        for (int k = 0; k < p.dk16; ++k) {
-          const uint32_t off = (k >> 2) * CHUNK_BYTES + (k & 3) * 32;
-          umma_bf16(tmem_S + (j & 1) * 128, make_sdesc_sw128(q_base + off, 16, 1024),
-                    make_sdesc_sw128(k_base + off, 16, 1024), idesc_qk, k != 0);
+    // The whole warp stays convergent (every lane polls the barriers, every lane computes the -- warp-uniform --
+    // descriptors) and only the tcgen05 instructions sit under elect.sync: the compiler keeps the operands in
+    // uniform registers instead of emitting a broadcast loop per MMA, which matters because one attention tile
+    // is 13 small MMAs (40-64 tensor-pipe clocks each) and their issue cost was the kernel's bottleneck.
+    const uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
+    const uint32_t idesc_pv = make_idesc_bf16(128, p.dk16 * 16, 0, 1);  // A = P from TMEM; B = V MN-major (d contiguous)
+    const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
+    const uint32_t stage_step = uint32_t(tile_bytes) >> 4;  // descriptor address field counts 16-byte units
+    const int dk16 = p.dk16;
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t kd = k_desc0 + uint64_t(st * stage_step);
+        const uint32_t sd = tmem_S + (j & 1) * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          if (k < dk16) {
+            const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
+            umma_bf16(sd, q_desc + off, kd + off, idesc_qk, k != 0);
+          }
         }
         umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < n_kv; ++j) {
-        // S((j+1)&1) still holds P(j-1): tcgen05.mma executes in issue order, so this S^T write follows P V (j-1)
-        if (j + 1 < n_kv) issue_qk(j + 1);
-        const int st = j & 1;
-        mbar_wait(p_full, j & 1);
-        mbar_wait(&v_full[st], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t v_base = smem_u32(sV + st * tile_bytes);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      // S((j+1)&1) still holds P(j-1): tcgen05.mma executes in issue order, so this S write follows P V (j-1)
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j & 1;
+      mbar_wait(p_full, j & 1);
+      mbar_wait(&v_full[st], (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t vd = v_desc0 + uint64_t(st * stage_step);
         const uint32_t p_addr = tmem_S + (j & 1) * 128;
 #pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k) {  // 16 keys = 8 packed TMEM columns per step
-          const uint64_t db = make_sdesc_sw128(v_base + k * 2048, CHUNK_BYTES, 1024);
-          umma_bf16_ts(tmem_O, p_addr + k * 8, db, idesc_pv, (j | k) != 0);
-        }
+        for (int k = 0; k < ATT_BN / 16; ++k)  // 16 keys = 8 packed TMEM columns = 2048 smem bytes per step
+          umma_bf16_ts(tmem_O, p_addr + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0);
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
-    // ===================== softmax / correction / epilogue (128 threads, thread == query row) =====================
-    const int tid = threadIdx.x;
-    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    // ===================== softmax / correction / epilogue (2 x 128 threads, thread == query row) =====================
+    const int row = threadIdx.x & 127;  // query row within the tile == TMEM lane
+    const int wg = threadIdx.x >> 7;    // 0: keys [0,64) of every tile, 1: keys [64,128)
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
+    // O columns this half rescales / writes out (8-column groups split between the two warpgroups)
+    const int og = (p.d + 7) / 8;
+    const int oc0 = wg == 0 ? 0 : ((og + 1) / 2) * 8, oc1 = wg == 0 ? ((og + 1) / 2) * 8 : p.d;
     float m_used = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
       const int buf = j & 1;
       const bool need_bias = p.bias != nullptr || (j + 1) * ATT_BN > p.Sk;  // CTA-uniform
       if (need_bias) {  // additive key bias (pre-multiplied by log2 e) and the key-padding mask of a ragged last tile
-        const int kv = j * ATT_BN + tid;
-        float bv = 0.f;
-        if (kv >= p.Sk) bv = -INFINITY;
-        else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
-        sBias[buf * 128 + tid] = bv;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (wg == 0) {
+          const int kv = j * ATT_BN + row;
+          float bv = 0.f;
+          if (kv >= p.Sk) bv = -INFINITY;
+          else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
+          sBias[buf * 128 + row] = bv;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
-      uint32_t sr[128];
-      tmem_ld32(s_addr, sr);
-      tmem_ld32(s_addr + 32, sr + 32);
-      tmem_ld32(s_addr + 64, sr + 64);
-      tmem_ld32(s_addr + 96, sr + 96);
-      tmem_ld_wait();
-      float mx = -INFINITY;
-      if (need_bias) {
-        const float* bias_s = sBias + buf * 128;
+      uint32_t sr[64];
+#ifdef TDM_DBG_NOLD
 #pragma unroll
-        for (int i = 0; i < 128; ++i) {
-          const float v = fmaf(__uint_as_float(sr[i]), p.scale_log2, bias_s[i]);
-          sr[i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+      for (int i = 0; i < 64; ++i) sr[i] = __float_as_uint(0.001f * (float)(i + row));
+#else
+      tmem_ld32(s_addr + wg * 64, sr);
+      tmem_ld32(s_addr + wg * 64 + 32, sr + 32);
+      tmem_ld_wait();
+#endif
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (need_bias) {
+        const float* bias_s = sBias + buf * 128 + wg * 64;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias_s + i);
+          const float v0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, bb.x), v1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, bb.y);
+          const float v2 = fmaf(__uint_as_float(sr[i + 2]), p.scale_log2, bb.z), v3 = fmaf(__uint_as_float(sr[i + 3]), p.scale_log2, bb.w);
+          sr[i] = __float_as_uint(v0); sr[i + 1] = __float_as_uint(v1); sr[i + 2] = __float_as_uint(v2); sr[i + 3] = __float_as_uint(v3);
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
-        mx *= p.scale_log2;  // scale > 0
+        for (int i = 0; i < 64; i += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[i])); mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+        }
       }
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (!need_bias) mx *= p.scale_log2;  // scale > 0
+      // exchange the half-row maxima (double-buffered by tile parity: one barrier per tile is enough)
+      float* mx_s = sMax + buf * 256;
+      mx_s[wg * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, mx_s[(wg ^ 1) * 128 + row]);
       // Lazy rescale: O and l keep the stale maximum until it is exceeded by more than 2^8 (exact after the final
-      // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform because tcgen05.ld/st are collective.
+      // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform (tcgen05.ld/st are collective) and
+      // identical in both warpgroups, which see the same rows and the same exchanged maxima.
       const float m_new = fmaxf(m_used, mx);
       if (j == 0) {
         m_used = m_new;
@@ -191,7 +231,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float alpha = ex2_fast(m_used - m_new);
         l_run *= alpha;
         m_used = m_new;
-        for (int c = 0; c < p.d; c += 8) {
+        for (int c = oc0; c < oc1; c += 8) {
           uint32_t r[8];
           tmem_ld8(tmem_O + lane_off + c, r);
           tmem_ld_wait();
@@ -203,39 +243,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_wait();
       }
       // P is packed in place: sr[i] <- bf16x2(p[2i], p[2i+1]) (the write index never passes the read index)
+      float l0 = 0.f, l1 = 0.f;
       if (need_bias) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < 32; ++i) {
           const float p0 = ex2_fast(__uint_as_float(sr[2 * i]) - m_used);
           const float p1 = ex2_fast(__uint_as_float(sr[2 * i + 1]) - m_used);
-          l_run += p0 + p1;
+          l0 += p0;
+          l1 += p1;
           sr[i] = pack_bf16(p0, p1);
         }
       } else {
         const float nm = -m_used;
 #pragma unroll
-        for (int i = 0; i < 64; ++i) {
+        for (int i = 0; i < 32; ++i) {
+#ifdef TDM_DBG_NOEXP
+          const float p0 = fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm);
+          const float p1 = fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm);
+#else
           const float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
           const float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
-          l_run += p0 + p1;
+#endif
+          l0 += p0;
+          l1 += p1;
           sr[i] = pack_bf16(p0, p1);
         }
       }
-      tmem_st32(s_addr, sr);
-      tmem_st32(s_addr + 32, sr + 32);
+      l_run += l0 + l1;
+#ifndef TDM_DBG_NOST
+      tmem_st32(s_addr + wg * 32, sr);
       tmem_st_wait();
+#endif
       tc_fence_before();
       mbar_arrive(p_full);
     }
+    // combine the two halves' row sums
+    float* l_s = sMax;  // free now: every thread is past the last exchange barrier... of the previous tile at least
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_s[wg * 128 + row] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l_run += l_s[(wg ^ 1) * 128 + row];
     mbar_wait(pv_done, (n_kv - 1) & 1);
     tc_fence_after();
-    const int q = q0 + tid;
+    const int q = q0 + row;
     const float inv_l = 1.f / l_run;
-    if (q < p.Sq) {
+    if (q < p.Sq && wg == 0) {
       if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_used + log2f(l_run)) * 0.6931471805599453f;
     }
     bf16* orow = p.O + (long)b * p.o_stride_b + (long)q * p.o_stride_s + (long)h * p.o_stride_h;
-    for (int c = 0; c < p.d; c += 8) {
+    for (int c = oc0; c < oc1; c += 8) {
       uint32_t r[8];
       tmem_ld8(tmem_O + lane_off + c, r);
       tmem_ld_wait();
@@ -251,7 +307,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -292,14 +348,14 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   p.bias = a->bias;
   p.O = (bf16*)a->O; p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.lse = a->lse;
-  const int smem = 5 * p.nd * CHUNK_BYTES + 1024 + 256 + 1024;
+  const int smem = 5 * p.nd * CHUNK_BYTES + 1024 + 2048 + 256 + 1024;
   static int smem_set = 0;
   if (smem > smem_set) {
     TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
   dim3 grid((a->Sq + ATT_BM - 1) / ATT_BM, a->H, a->B);
-  ::tdm::count_launch(); attn_fwd_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  ::tdm::count_launch(); attn_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

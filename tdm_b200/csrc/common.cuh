@@ -96,6 +96,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling an mbarrier costs issue slots and XU-pipe cycles that the math warps of the same SM need (ncu: the
+// spin loops of waiting warps kept the XU pipe 60-75 % busy in the attention kernels).  Everything that is not the
+// single MMA-issuing thread waits with a nanosleep back-off instead of a tight spin.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(spins < 8 ? 40 : 200);
+    if (++spins > (1u << 23)) {
+      printf("tdm: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -292,6 +307,23 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   float x2 = x * x;
   float t = tanhf(k0 * (x + k1 * x * x2));
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x2);
+}
+// exp2 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], relative error
+// ~1e-4: far below bf16 resolution): lets the softmax kernels move part of their exponentials off the XU pipe.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float magic = 12582912.f;  // 1.5 * 2^23: x + magic rounds x to the nearest integer in the low mantissa bits
+  const float xr = x + magic;
+  const float f = x - (xr - magic);  // in [-0.5, 0.5]
+  float pz = fmaf(f, 0.05550410866f, 0.2402265070f);
+  pz = fmaf(pz, f, 0.6931471806f);
+  pz = fmaf(pz, f, 1.0f);
+  return __uint_as_float(__float_as_uint(pz) + (__float_as_uint(xr) << 23));
+}
+// bf16x2 pack with integer round-half-up (ALU pipe) instead of the F2FP conversion
+__device__ __forceinline__ uint32_t pack_bf16_alu(float a, float b) {
+  const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+  return __byte_perm(ua, ub, 0x7632);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
