@@ -99,6 +99,7 @@ typedef struct TdmGemm {
   int64_t ld_out_bf16;
   int32_t tile_n;  /* 0 = choose; else 64/128/192/256 */
   int32_t split_k; /* 0 = choose; >1 forces split-K (accumulate-only epilogues: res == out_f32, nothing else) */
+  int32_t cta_pair; /* 0 = choose; 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per 256-row tile */
 } TdmGemm;
 
 int tdm_gemm_bf16(const TdmGemm* g, void* stream);

@@ -23,7 +23,7 @@ def timeit(fn, iters=20, warm=3):
     return e0.elapsed_time(e1) / iters * 1e3  # us
 
 
-def gemm_case(name, M, N, K, epi, tile_n=0):
+def gemm_case(name, M, N, K, epi, tile_n=0, cta_pair=0):
     B, T = 8, M // 8
     a = [torch.randn(M, K, device=DEV).bfloat16() for _ in range(NB)]
     w = [(torch.randn(N, K, device=DEV) * 0.05).bfloat16() for _ in range(NB)]
@@ -44,8 +44,8 @@ def gemm_case(name, M, N, K, epi, tile_n=0):
         "res": lambda i: dict(bias=bias, res=res[i], out_f32=o32[i]),
         "res_inplace": lambda i: dict(res=o32[i], out_f32=o32[i]),
     }[epi]
-    us = timeit(lambda i: ops.gemm(a[i % NB], w[i % NB], tile_n=tile_n, **kw(i % NB)))
-    print(json.dumps({"kernel": "gemm", "case": name, "epi": epi, "M": M, "N": N, "K": K, "tile_n": tile_n, "us": round(us, 2),
+    us = timeit(lambda i: ops.gemm(a[i % NB], w[i % NB], tile_n=tile_n, cta_pair=cta_pair, **kw(i % NB)))
+    print(json.dumps({"kernel": "gemm", "case": name, "epi": epi, "M": M, "N": N, "K": K, "tile_n": tile_n, "cta_pair": cta_pair, "us": round(us, 2),
                       "tflops": round(2.0 * M * N * K / us / 1e6, 1)}), flush=True)
 
 
@@ -106,6 +106,13 @@ def ln_case(M, D):
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gemm", "wgrad", "attn", "ln"]
     M, D = 8192, 1152
+    if "pair" in which:
+        for nm, (m, n, k), epi in (("qkv", (M, 3 * D, D), "bias"), ("q2", (M, D, D), "bias"), ("o_proj", (M, D, D), "gate_res_2out"),
+                                   ("ff1", (M, 4 * D, D), "gelu"), ("ff1_plain", (M, 4 * D, D), "plain"), ("ff2", (M, D, 4 * D), "gate_res"),
+                                   ("big", (8192, 8192, 8192), "plain")):
+            for pr in (1, 2):
+                for tn in (128, 192, 256):
+                    gemm_case(nm, m, n, k, epi, tn, pr)
     if "gemm" in which:
         gemm_case("qkv", M, 3 * D, D, "bias")
         gemm_case("qkv_192", M, 3 * D, D, "bias", 192)

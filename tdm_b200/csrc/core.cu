@@ -55,6 +55,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int make_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz) {
+  return make_tma_typed(map, base, 0, rank, dims, strides_bytes, box, swz);
+}
+
+int make_tma_typed(CUtensorMap* map, const void* base, int is_f32, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box, TmaSwizzle swz) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(TDM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint64_t gdims[5];
@@ -70,7 +75,7 @@ int make_tma_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   if (swz == TMA_SWZ_32) s = CU_TENSOR_MAP_SWIZZLE_32B;
   if (swz == TMA_SWZ_64) s = CU_TENSOR_MAP_SWIZZLE_64B;
   if (swz == TMA_SWZ_128) s = CU_TENSOR_MAP_SWIZZLE_128B;
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
+  CUresult r = fn(map, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
                   gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, s, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

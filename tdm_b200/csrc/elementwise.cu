@@ -14,6 +14,7 @@ constexpr int LN_MAXV = 16;  // float4 per lane: D <= 2048
 // h = LN(x) * (1 + scale[b]) + shift[b]   (no affine, eps inside sqrt), x fp32 -> h bf16.
 // One warp per row, row held in registers, two-pass mean / variance in fp32.
 // ---------------------------------------------------------------------------------------------
+template <int NV>  // float4 per lane actually used (D == NV * 128), or 0: runtime count up to LN_MAXV
 __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __restrict__ x, const float* __restrict__ shift,
                                                             const float* __restrict__ scale, long mod_stride,
                                                             int rows_per_sample, bf16* __restrict__ out,
@@ -22,7 +23,8 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __res
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;  // float4 per lane
+  constexpr int LN_MAXV = NV > 0 ? NV : tdm::LN_MAXV;  // shadows the global bound: registers sized to the real row
+  const int nv = NV > 0 ? NV : (D >> 7);               // float4 per lane
   const float4* xr = reinterpret_cast<const float4*>(x + (long)row * D);
   float4 v[LN_MAXV];
   float s = 0.f;
@@ -61,6 +63,7 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __res
 }
 
 // dx_out = dx_in + rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dh * (1 + scale[b])
+template <int NV>
 __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __restrict__ dh, const float* __restrict__ x,
                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                             const float* __restrict__ scale, long mod_stride, int rows_per_sample,
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const int nv = D >> 7;
+  constexpr int LN_MAXV = NV > 0 ? NV : tdm::LN_MAXV;
+  const int nv = NV > 0 ? NV : (D >> 7);
   const float mean = mean_in[row], rstd = rstd_in[row];
   const float4* xr = reinterpret_cast<const float4*>(x + (long)row * D);
   const uint2* dr = reinterpret_cast<const uint2*>(dh + (long)row * D);
@@ -341,8 +345,15 @@ extern "C" int tdm_ln_modulate_fwd(const float* x, const float* shift, const flo
   TDM_REQUIRE(x && shift && scale && out_bf16, "tdm_ln_modulate_fwd: null input");
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_fwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE(M > 0 && rows_per_sample > 0 && mod_stride % 4 == 0, "tdm_ln_modulate_fwd: bad shape");
-  ::tdm::count_launch(); ln_modulate_fwd_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, shift, scale, mod_stride, rows_per_sample,
-                                                                      (bf16*)out_bf16, mean, rstd, M, D, eps);
+  ::tdm::count_launch();
+#define TDM_LN_FWD(NVV) ln_modulate_fwd_kernel<NVV><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>( \
+      x, shift, scale, mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, D, eps)
+  switch (D >> 7) {
+    case 2: TDM_LN_FWD(2); break;
+    case 9: TDM_LN_FWD(9); break;
+    default: TDM_LN_FWD(0); break;
+  }
+#undef TDM_LN_FWD
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -355,8 +366,15 @@ extern "C" int tdm_ln_modulate_bwd(const void* dh_bf16, const float* x, const fl
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_bwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE((dshift == nullptr) == (dscale == nullptr), "tdm_ln_modulate_bwd: dshift and dscale come together");
   cudaStream_t s = (cudaStream_t)stream;
-  ::tdm::count_launch(); ln_modulate_bwd_kernel<<<(M + 7) / 8, 256, 0, s>>>((const bf16*)dh_bf16, x, mean, rstd, scale, mod_stride,
-                                                    rows_per_sample, dx_in, dx_out, (bf16*)dx_out_bf16, M, D);
+  ::tdm::count_launch();
+#define TDM_LN_BWD(NVV) ln_modulate_bwd_kernel<NVV><<<(M + 7) / 8, 256, 0, s>>>( \
+      (const bf16*)dh_bf16, x, mean, rstd, scale, mod_stride, rows_per_sample, dx_in, dx_out, (bf16*)dx_out_bf16, M, D)
+  switch (D >> 7) {
+    case 2: TDM_LN_BWD(2); break;
+    case 9: TDM_LN_BWD(9); break;
+    default: TDM_LN_BWD(0); break;
+  }
+#undef TDM_LN_BWD
   TDM_CHECK_CUDA(cudaGetLastError());
   if (dshift) {
     ColRedArgs a = {};

@@ -45,18 +45,27 @@ struct GemmParams {
 };
 
 constexpr int EPI_WARPS = 8;   // two warps per TMEM lane quarter, each takes every other 32-column chunk of the tile
-constexpr int EPI_PITCH = 36;  // floats per staged row (32 + 4 pad): conflict-free 128-bit row writes and 64-bit column reads
 constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+
+// Epilogue shared memory: per epilogue warp one 32-row x 32-column staging tile for each output precision (fp32 with
+// the 128-byte swizzle, bf16 with the 64-byte swizzle) that a TMA store drains -- every HBM write is a full line and
+// the LSU only sees conflict-free 16-byte shared-memory stores -- plus the tile's bias / gate rows, staged once per
+// tile by all epilogue warps BEFORE they wait for the accumulator (their latency hides behind the mainloop).
+constexpr int EPI_STAGE_F32 = 32 * 32 * 4;                        // 4 KB
+constexpr int EPI_STAGE_BF16 = 32 * 32 * 2;                       // 2 KB
+constexpr int EPI_STAGE_WARP = EPI_STAGE_F32 + EPI_STAGE_BF16;    // 6 KB per warp
+constexpr int EPI_VEC_FLOATS = 256;                               // >= widest tile
+constexpr int EPI_SMEM_BYTES = EPI_WARPS * EPI_STAGE_WARP + 2 * 2 * EPI_VEC_FLOATS * 4;  // 48 KB + 4 KB
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 192 ? 4 : (BN >= 128 ? 5 : 7));  // 52 KB go to the epilogue
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int STAGING_BYTES = 0;
+  static constexpr int STAGING_BYTES = EPI_SMEM_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
 };
@@ -72,16 +81,156 @@ __device__ __forceinline__ float gelu_tanh_grad_fast(float x) {
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x2);
 }
 
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }
+
+// All epilogue warps: stage bias[n0 .. n0+BN) and (per-tile uniform) gate[n0 .. n0+BN) into buffer `as`.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_stage_vectors(const GemmParams& p, float* svec, int as, int m0, int n0, int et) {
+  float* sb = svec + as * 2 * EPI_VEC_FLOATS;
+  float* sg = sb + EPI_VEC_FLOATS;
+  const float* gate_tile = (p.gate && p.gate_uniform) ? p.gate + (long)(m0 / p.rows_per_gate) * p.gate_stride : nullptr;
+  for (int n = et; n < BN; n += 32 * EPI_WARPS) {
+    const bool ok = n0 + n < p.N;
+    sb[n] = (p.bias && ok) ? p.bias[n0 + n] : 0.f;
+    sg[n] = (gate_tile && ok) ? gate_tile[n0 + n] : 1.f;
+  }
+  epi_barrier();
+}
+
+// Fused epilogue of one 128-row accumulator quarter: thread == accumulator row (tcgen05.ld 32x32b), so the 32 values
+// of a chunk sit in registers (32-way ILP).  `q` = TMEM lane quarter of the calling warp, `ch` = even / odd chunks.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CUtensorMap* tmC16, const CUtensorMap* tmC32,
+                                                   uint32_t taddr, int m0, int n0, int q, int ch, int lane, uint8_t* stg,
+                                                   const float* svec, int as) {
+  const int m = m0 + q * 32 + lane;
+  const bool row_ok = m < p.M;
+  const float* sb = svec + as * 2 * EPI_VEC_FLOATS;
+  const float* sg = sb + EPI_VEC_FLOATS;
+  const float* gate_row = nullptr;  // only when the gate changes inside a tile
+  if (p.gate && !p.gate_uniform && row_ok) gate_row = p.gate + (long)(m / p.rows_per_gate) * p.gate_stride;
+  const long rr = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
+  uint8_t* stg_f = stg + lane * 128;                      // fp32 row (128 B, SW128: unit ^= row & 7)
+  uint8_t* stg_h = stg + EPI_STAGE_F32 + lane * 64;       // bf16 row (64 B, SW64: unit ^= (row >> 1) & 3)
+  const int xf = lane & 7, xh = (lane >> 1) & 3;
+#pragma unroll 1
+  for (int c = ch * 32; c < BN; c += 64) {
+    if (n0 + c >= p.N) break;  // warp-uniform
+    uint32_t acc[32];
+    tmem_ld32(taddr + c, acc);
+    tmem_ld_wait();
+    if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
+      if (row_ok) {
+        float* o = p.out_f32 + (long)m * p.ld_out_f32 + n0 + c;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + c + i < p.N) atomicAdd(o + i, p.alpha * __uint_as_float(acc[i]));
+      }
+      continue;
+    }
+    // the TMA engine may still be reading this warp's staging tiles for the previous chunk
+    if (lane == 0) tma_store_wait_read();
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int n = n0 + c + g * 8;
+      const bool ok = row_ok && n < p.N;  // guards every direct global access; staged stores are clipped by the TMA
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(acc[g * 8 + i]);
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(sb + c + g * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sb + c + g * 8 + 4);
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.pre_out && ok) {
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+        o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.pre_out + (long)m * p.ld_pre + n) = o;
+      }
+      if (p.pre_out_f32 && ok) {
+        float* o = p.pre_out_f32 + (long)m * p.ld_pre_f32 + n;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (p.act == TDM_ACT_GELU_TANH) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_fast(v[i]);
+      } else if (p.act == TDM_ACT_GELU_TANH_BWD) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (ok) u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+        const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+        v[0] *= gelu_tanh_grad_fast(u0.x); v[1] *= gelu_tanh_grad_fast(u0.y);
+        v[2] *= gelu_tanh_grad_fast(u1.x); v[3] *= gelu_tanh_grad_fast(u1.y);
+        v[4] *= gelu_tanh_grad_fast(u2.x); v[5] *= gelu_tanh_grad_fast(u2.y);
+        v[6] *= gelu_tanh_grad_fast(u3.x); v[7] *= gelu_tanh_grad_fast(u3.y);
+      } else if (p.act == TDM_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+      } else if (p.act == TDM_ACT_SILU_BWD) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (ok) u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
+        const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
+        const float uu[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float sgm = 1.f / (1.f + __expf(-uu[i]));
+          v[i] *= sgm * (1.f + uu[i] * (1.f - sgm));
+        }
+      }
+      if (p.gate) {
+        float4 g0, g1;
+        if (gate_row) {
+          g0 = ok ? *reinterpret_cast<const float4*>(gate_row + n) : make_float4(1, 1, 1, 1);
+          g1 = ok ? *reinterpret_cast<const float4*>(gate_row + n + 4) : make_float4(1, 1, 1, 1);
+        } else {
+          g0 = *reinterpret_cast<const float4*>(sg + c + g * 8);
+          g1 = *reinterpret_cast<const float4*>(sg + c + g * 8 + 4);
+        }
+        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+        v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+      }
+      if (p.res && ok) {
+        const float4 r0 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n);
+        const float4 r1 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n + 4);
+        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
+        v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+      }
+      if (p.out_f32) {
+        *reinterpret_cast<float4*>(stg_f + (((2 * g) ^ xf) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(stg_f + (((2 * g + 1) ^ xf) << 4)) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      if (p.out_bf16) {
+        uint4 o;
+        o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
+        o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+        *reinterpret_cast<uint4*>(stg_h + ((g ^ xh) << 4)) = o;
+      }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (p.out_f32) tma_store_2d(tmC32, stg, n0 + c, m0 + q * 32);
+      if (p.out_bf16) tma_store_2d(tmC16, stg + EPI_STAGE_F32, n0 + c, m0 + q * 32);
+      tma_store_commit();
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
                  const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* staging = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned: stages are multiples of 8 KB
+  float* epi_vec = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_STAGE_WARP);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -135,6 +284,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
+#ifdef TDM_DBG_NOTMA
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+#endif
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const CUtensorMap* mA = &tmA;
           const CUtensorMap* mB = &tmB;
@@ -192,7 +346,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+#ifndef TDM_DBG_NOMMA
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k != 0));
+#endif
           }
           umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == STAGES) {
@@ -217,105 +373,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t aphase = (it >> 1) & 1;
       const int m0 = (tile / p.num_n_tiles) * BM;
       const int n0 = (tile % p.num_n_tiles) * BN;
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
+      gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
-      const float* gate_row = nullptr;
-      if (p.gate && row_ok) gate_row = p.gate + (long)(m / p.rows_per_gate) * p.gate_stride;
-      const long rr = p.res_row_mod > 0 ? (m % p.res_row_mod) : m;
-#pragma unroll 1
-      for (int c = ch * 32; c < BN; c += 64) {
-        if (n0 + c >= p.N) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld32(taddr + c, acc);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
-          float* o = p.out_f32 + (long)m * p.ld_out_f32 + n0 + c;
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + c + i < p.N) atomicAdd(o + i, p.alpha * __uint_as_float(acc[i]));
-          continue;
-        }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c + g * 8;
-          if (n < p.N) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(acc[g * 8 + i]);
-            if (p.bias) {
-              const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-            }
-            if (p.pre_out) {
-              uint4 o;
-              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.pre_out + (long)m * p.ld_pre + n) = o;
-            }
-            if (p.pre_out_f32) {
-              float* o = p.pre_out_f32 + (long)m * p.ld_pre_f32 + n;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (p.act == TDM_ACT_GELU_TANH) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = gelu_tanh_fast(v[i]);
-            } else if (p.act == TDM_ACT_GELU_TANH_BWD) {
-              const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
-              const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
-              v[0] *= gelu_tanh_grad_fast(u0.x); v[1] *= gelu_tanh_grad_fast(u0.y);
-              v[2] *= gelu_tanh_grad_fast(u1.x); v[3] *= gelu_tanh_grad_fast(u1.y);
-              v[4] *= gelu_tanh_grad_fast(u2.x); v[5] *= gelu_tanh_grad_fast(u2.y);
-              v[6] *= gelu_tanh_grad_fast(u3.x); v[7] *= gelu_tanh_grad_fast(u3.y);
-            } else if (p.act == TDM_ACT_SILU) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
-            } else if (p.act == TDM_ACT_SILU_BWD) {
-              const uint4 u = *reinterpret_cast<const uint4*>(p.act_in + (long)m * p.ld_act + n);
-              const float2 u0 = unpack_bf16(u.x), u1 = unpack_bf16(u.y), u2 = unpack_bf16(u.z), u3 = unpack_bf16(u.w);
-              const float uu[8] = {u0.x, u0.y, u1.x, u1.y, u2.x, u2.y, u3.x, u3.y};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const float sg = 1.f / (1.f + __expf(-uu[i]));
-                v[i] *= sg * (1.f + uu[i] * (1.f - sg));
-              }
-            }
-            if (gate_row) {
-              const float4 g0 = *reinterpret_cast<const float4*>(gate_row + n);
-              const float4 g1 = *reinterpret_cast<const float4*>(gate_row + n + 4);
-              v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-              v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-            }
-            if (p.res) {
-              const float4 r0 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n);
-              const float4 r1 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n + 4);
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-              v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-            }
-            if (p.out_f32) {
-              float* o = p.out_f32 + (long)m * p.ld_out_f32 + n;
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            }
-            if (p.out_bf16) {
-              uint4 o;
-              o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
-              o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-              *reinterpret_cast<uint4*>(p.out_bf16 + (long)m * p.ld_out_bf16 + n) = o;
-            }
-          }
-        }
-      }
+#ifndef TDM_DBG_NOEPI
+      gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
     }
+    if (lane == 0) tma_store_wait_all();  // the staging tiles must outlive the bulk stores that read them
   }
 
   tc_fence_before();
@@ -323,6 +392,201 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256 x BN output tile per pair of SMs.  Each CTA stages its own 128 rows of A
+// and HALF of the B tile, the leader CTA's single thread issues 256 x BN x 16 MMAs that read both CTAs' shared
+// memory and write both CTAs' tensor memory.  Per CTA and 64-deep k-block that is (128 + BN/2) * 128 bytes of
+// L2 -> SMEM traffic instead of (128 + BN) * 128: the mainloop of the single-CTA kernel is bound by exactly that
+// stream (B300_MICROARCH.md: chip-wide LTS cap ~6300 B/clk), so the pair runs ~1.4x closer to the tensor peak.
+// Barriers: `full` lives in the leader (both CTAs' TMA loads credit it), `empty` / `tfull` are signalled in both
+// CTAs by multicast tcgen05.commit, `tempty` lives in the leader (the peer's epilogue warps arrive remotely).
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the N extent
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 5 : (BN >= 192 ? 6 : 7);
+  static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
+                  const GemmParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned: stages are multiples of 4 KB... see assert
+  static_assert((STAGES * Cfg::STAGE_BYTES) % 1024 == 0, "epilogue staging must stay 1024-byte aligned");
+  float* epi_vec = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_STAGE_WARP);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_SMEM_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int nk1 = (p.K + BK - 1) / BK;
+  const int nk2 = (p.K2 + BK - 1) / BK;
+  const int nk = nk1 + nk2;
+  const int num_units = p.num_m_tiles * p.num_n_tiles * p.splits;  // num_m_tiles counts 256-row pair tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (nk2) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers and tensor memory exist before anyone signals or writes across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = pair; unit < num_units; unit += npairs) {
+        const int tile = unit / p.splits, sp = unit - tile * p.splits;
+        const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        const int nh = n0 + (int)rank * (BN / 2);  // this CTA's half of the B tile
+        const int seg = p.seg_n > 0 ? n0 / p.seg_n : 0;
+        const int kb0 = (int)((long)sp * nk / p.splits), kb1 = (int)((long)(sp + 1) * nk / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sB = sA + Cfg::A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const uint32_t fb = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;  // the leader's barrier, from either CTA
+          const CUtensorMap* mA = &tmA;
+          const CUtensorMap* mB = &tmB;
+          int ka = kb * BK, kbb = kb * BK;
+          if (kb >= nk1) {
+            mA = &tmA2;
+            mB = &tmB2;
+            kbb = (kb - nk1) * BK;
+            ka = seg * p.seg_k2 + kbb;
+          }
+          if (!p.a_mn) {
+            tma_load_2d_2cta(sA, mA, fb, ka, m0);
+          } else {
+            tma_load_2d_2cta(sA, mA, fb, m0, ka);
+            tma_load_2d_2cta(sA + 8192, mA, fb, m0 + 64, ka);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2cta(sB, mB, fb, kbb, nh);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j) tma_load_2d_2cta(sB + j * 8192, mB, fb, nh + 64 * j, kbb);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only; warp-convergent, tcgen05 ops under elect.sync) =====================
+    if (leader) {
+      const uint32_t idesc = make_idesc_bf16(2 * BM, BN, p.a_mn, p.b_mn);
+      const uint32_t a_kstep = (p.a_mn ? 2048u : 32u) >> 4;  // descriptor address units (16 B) per UMMA_K = 16
+      const uint32_t b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
+      const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem), a_lbo, 1024);
+      const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem) + Cfg::A_BYTES, b_lbo, 1024);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+        const int tile = unit / p.splits, sp = unit - tile * p.splits;
+        const int kb0 = (int)((long)sp * nk / p.splits), kb1 = (int)((long)(sp + 1) * nk / p.splits);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t da = a_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
+            const uint64_t db = b_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_2cta(tmem_d, da + uint64_t(k * a_kstep), db + uint64_t(k * b_kstep), idesc, (kb > kb0) || (k != 0));
+            umma_commit_2cta(&empty_bar[stage]);  // frees the stage in BOTH CTAs when these MMAs retire
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit_2cta(&tfull_bar[as]);  // accumulator complete, both CTAs' epilogues may read
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: each owns its 128 accumulator rows) =====================
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int ch = ew >> 2;
+    int it = 0;
+    for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+      const int tile = unit / p.splits;
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % p.num_n_tiles) * BN;
+      gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
+      gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[as]) & PEER_BIT_MASK);  // the leader's barrier
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -349,26 +613,42 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, lon
   return make_tma_bf16(map, ptr, 2, dims, strides, box, TMA_SWZ_128);
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  constexpr int SMEM = PAIR ? Gemm2Cfg<BN>::SMEM_BYTES : GemmCfg<BN>::SMEM_BYTES;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;   // rows of one work unit
+  constexpr int BOX_N = PAIR ? BN / 2 : BN;    // B rows one CTA stages per k-block
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
   if ((rc = make_operand_map(&tmA, g->A, g->a_mn_major, g->M, g->K, g->lda, BM))) return rc;
-  if ((rc = make_operand_map(&tmB, g->B, g->b_mn_major, g->N, g->K, g->ldb, BN))) return rc;
+  if ((rc = make_operand_map(&tmB, g->B, g->b_mn_major, g->N, g->K, g->ldb, BOX_N))) return rc;
   if (g->K2 > 0) {
     const long a2_cols = g->seg_n > 0 ? (long)((g->N + g->seg_n - 1) / g->seg_n) * g->seg_k2 : g->K2;
     if ((rc = make_operand_map(&tmA2, g->A2, g->a_mn_major, g->M, a2_cols, g->lda2, BM))) return rc;
-    if ((rc = make_operand_map(&tmB2, g->B2, g->b_mn_major, g->N, g->K2, g->ldb2, BN))) return rc;
+    if ((rc = make_operand_map(&tmB2, g->B2, g->b_mn_major, g->N, g->K2, g->ldb2, BOX_N))) return rc;
   } else {
     tmA2 = tmA;
     tmB2 = tmB;
+  }
+  // output tensor maps for the TMA-store epilogue: [M, N] row-major, 32 x 32 boxes
+  CUtensorMap tmC16 = tmA, tmC32 = tmA;
+  {
+    const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+    const uint32_t box[2] = {32, 32};
+    if (g->out_bf16) {
+      const uint64_t st[1] = {(uint64_t)g->ld_out_bf16 * 2};
+      if ((rc = make_tma_typed(&tmC16, g->out_bf16, 0, 2, dims, st, box, TMA_SWZ_64))) return rc;
+    }
+    if (g->out_f32) {
+      const uint64_t st[1] = {(uint64_t)g->ld_out_f32 * 4};
+      if ((rc = make_tma_typed(&tmC32, g->out_f32, 1, 2, dims, st, box, TMA_SWZ_128))) return rc;
+    }
   }
   GemmParams p;
   p.M = g->M; p.N = g->N; p.K = g->K; p.K2 = g->K2 > 0 ? g->K2 : 0;
   p.a_mn = g->a_mn_major; p.b_mn = g->b_mn_major;
   p.seg_n = g->seg_n; p.seg_k2 = g->seg_k2;
-  p.num_m_tiles = (g->M + BM - 1) / BM;
+  p.num_m_tiles = (g->M + TILE_M - 1) / TILE_M;
   p.num_n_tiles = (g->N + BN - 1) / BN;
   p.alpha = g->alpha; p.act = g->act; p.bias = g->bias;
   p.act_in = (const bf16*)g->act_in; p.ld_act = g->ld_act;
@@ -390,7 +670,7 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
     const int tiles0 = p.num_m_tiles * p.num_n_tiles;
     const int nk = (p.K + BK - 1) / BK;
     int want = g->split_k;
-    if (want == 0 && acc_only && tiles0 * 2 <= num_sms() && nk >= 16) {
+    if (want == 0 && acc_only && tiles0 * 4 <= num_sms() && nk >= 16) {  // only when the output is a handful of tiles
       want = (2 * num_sms() + tiles0 - 1) / tiles0;  // ~2 work units per SM
       if (want > nk / 4) want = nk / 4;              // keep >= 4 k-blocks per unit
     }
@@ -402,15 +682,23 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   }
 
   static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int sms = num_sms();
-  const int grid = units < sms ? units : sms;
-  ::tdm::count_launch(); gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA2, tmB2, p);
+  if constexpr (PAIR) {
+    if (!attr_set) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      attr_set = true;
+    }
+    const int pairs = units < sms / 2 ? units : sms / 2;
+    ::tdm::count_launch(); gemm2_bf16_kernel<BN><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC16, tmC32, p);
+  } else {
+    if (!attr_set) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+      attr_set = true;
+    }
+    const int grid = units < sms ? units : sms;
+    ::tdm::count_launch(); gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC16, tmC32, p);
+  }
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -442,40 +730,67 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
                   (!g->pre_out_f32 || g->ld_pre_f32 % 4 == 0) &&
                   (!g->act_in || g->ld_act % 8 == 0) && (!g->gate || g->gate_stride % 4 == 0),
               "tdm_gemm_bf16: epilogue leading dimensions must keep 16-byte alignment");
+  // Tile / mode choice, calibrated on B200 measurements (scripts/bench_kernels.py, profiles/): the mainloop of a
+  // 128 x BN tile costs ~ (BN + 64) per k-block (wider tiles amortise the A operand and the per-tile ramp), times the
+  // number of waves over the SMs (single CTA) or SM pairs.  The CTA-pair kernel only pays off for long-K, large
+  // problems with K-major operands (8192^3: 1424 vs 1280 TFLOP/s); at the model's K = 1152 the two are equal, so
+  // the simpler single-CTA kernel is the default there.
+  const int sms = num_sms();
   int bn = g->tile_n;
-  if (bn == 0) {
-    // Cost per 64-deep k-block, in SM clocks: the mainloop is bound either by the L2->SMEM operand stream
-    // (chip-wide ~6300 B/clk, B300_MICROARCH.md "LTS throughput cap": every tile pulls (128+BN)*128 bytes) or by
-    // the tensor pipe of the busiest SM (waves * 2*BN clocks for a 128xBNx64 slab).
-    const int sms = num_sms();
-    const long mt = (g->M + BM - 1) / BM;
-    auto cost = [&](int b) {
-      const long t = mt * ((g->N + b - 1) / b);
-      const long waves = (t + sms - 1) / sms;
-      const double bw = double(t) * double(128 + b) * 128.0 / 6300.0;
-      const double mma = double(waves) * 2.0 * double(b);
-      return bw > mma ? bw : mma;
-    };
+  int pair = g->cta_pair;  // 0 choose, 1 single CTA, 2 CTA pair
+  TDM_REQUIRE(pair >= 0 && pair <= 2, "tdm_gemm_bf16: cta_pair must be 0 (choose), 1 (single) or 2 (pair)");
+  if (pair == 0) pair = (g->K >= 4096 && g->M >= 2048 && g->N >= 2048 && !g->a_mn_major && !g->b_mn_major) ? 2 : 1;
+  auto cost = [&](int b, bool pr) {
+    const long mt = pr ? (g->M + 255) / 256 : (g->M + 127) / 128;
+    const long t = mt * ((g->N + b - 1) / b);
+    const long slots = pr ? sms / 2 : sms;
+    const long waves = (t + slots - 1) / slots;
+    return double(waves) * double(b + 64);
+  };
+  auto allowed = [&](int b, bool pr) {
+    if (g->seg_n > 0 && g->seg_n % b != 0) return false;
+    if (pr && (b < 128 || g->M <= 128)) return false;
+    if (pr && g->b_mn_major && b % 128 != 0) return false;  // each CTA stages whole 64-column groups of its half
+    return true;
+  };
+  if (bn == 0 || pair == 0) {
     const int cands[4] = {192, 256, 128, 64};  // ties go to 192: measured faster than 256 at N = 1152 / 3456
     double best = 1e30;
-    bn = 256;
-    for (int i = 0; i < 4; ++i) {
-      const int b = cands[i];
-      if (g->seg_n > 0 && g->seg_n % b != 0) continue;
-      const double c = cost(b);
-      if (c < best * 0.97) {  // prefer the wider tile unless the narrower one is clearly better
-        best = c;
-        bn = b;
+    int best_bn = 0, best_pair = 1;
+    for (int pm = 2; pm >= 1; --pm) {
+      if (pair != 0 && pair != pm) continue;
+      for (int i = 0; i < 4; ++i) {
+        const int b = cands[i];
+        if (bn != 0 && b != bn) continue;
+        if (!allowed(b, pm == 2)) continue;
+        const double c = cost(b, pm == 2);
+        if (c < best * 0.97) {  // prefer the earlier candidate unless a later one is clearly better
+          best = c;
+          best_bn = b;
+          best_pair = pm;
+        }
       }
     }
+    TDM_REQUIRE(best_bn != 0, "tdm_gemm_bf16: no tile configuration fits tile_n=%d cta_pair=%d seg_n=%d", g->tile_n, g->cta_pair, g->seg_n);
+    bn = best_bn;
+    pair = best_pair;
   }
-  if (g->seg_n > 0) TDM_REQUIRE(g->seg_n % bn == 0, "tdm_gemm_bf16: seg_n=%d must be a multiple of tile_n=%d", g->seg_n, bn);
+  TDM_REQUIRE(allowed(bn, pair == 2), "tdm_gemm_bf16: tile_n=%d cta_pair=%d not valid for this problem (seg_n=%d, M=%d, b_mn=%d)", bn, pair,
+              g->seg_n, g->M, g->b_mn_major);
   cudaStream_t s = (cudaStream_t)stream;
+  if (pair == 2) {
+    switch (bn) {
+      case 128: return launch_gemm<128, true>(g, s);
+      case 192: return launch_gemm<192, true>(g, s);
+      case 256: return launch_gemm<256, true>(g, s);
+      default: return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: CTA-pair tiles are 128, 192 or 256 wide (got %d)", bn);
+    }
+  }
   switch (bn) {
-    case 64: return launch_gemm<64>(g, s);
-    case 128: return launch_gemm<128>(g, s);
-    case 192: return launch_gemm<192>(g, s);
-    case 256: return launch_gemm<256>(g, s);
+    case 64: return launch_gemm<64, false>(g, s);
+    case 128: return launch_gemm<128, false>(g, s);
+    case 192: return launch_gemm<192, false>(g, s);
+    case 256: return launch_gemm<256, false>(g, s);
     default: return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: tile_n must be 0, 64, 128, 192 or 256 (got %d)", bn);
   }
 }

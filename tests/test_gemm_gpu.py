@@ -18,10 +18,13 @@ def _close(got, ref, tol, what=""):
     assert err / den <= tol, f"{what}: max abs err {err:.4g} / max ref {den:.4g} = {err/den:.3g} > {tol}"
 
 
+@pytest.mark.parametrize("cta_pair", [1, 2])
 @pytest.mark.parametrize("tile_n", [64, 128, 192, 256])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-def test_gemm_majors(tile_n, a_mn, b_mn):
+def test_gemm_majors(tile_n, a_mn, b_mn, cta_pair):
     from tdm_b200 import ops
+    if cta_pair == 2 and (tile_n == 64 or (b_mn and tile_n == 192)):
+        pytest.skip("not a CTA-pair configuration")
     M, N, K = 384, 512, 320
     a = _mk((M, K), seed=1)
     b = _mk((N, K), seed=2)
@@ -29,24 +32,29 @@ def test_gemm_majors(tile_n, a_mn, b_mn):
     a_s = a.t().contiguous() if a_mn else a
     b_s = b.t().contiguous() if b_mn else b
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
-    ops.gemm(a_s, b_s, a_mn_major=a_mn, b_mn_major=b_mn, out_f32=out, tile_n=tile_n)
+    ops.gemm(a_s, b_s, a_mn_major=a_mn, b_mn_major=b_mn, out_f32=out, tile_n=tile_n, cta_pair=cta_pair)
     torch.cuda.synchronize()
     _close(out, ref, 1e-5 * K ** 0.5 + 1e-4, f"majors a_mn={a_mn} b_mn={b_mn} bn={tile_n}")
 
 
-@pytest.mark.parametrize("M,N,K", [(100, 72, 40), (8192, 1152, 1152), (960, 2304, 1152), (130, 264, 4096), (512, 32, 256)])
-def test_gemm_shapes_and_tails(M, N, K):
+@pytest.mark.parametrize("cta_pair", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(100, 72, 40), (8192, 1152, 1152), (960, 2304, 1152), (130, 264, 4096), (512, 32, 256),
+                                   (8192, 4608, 1152), (1000, 1152, 200)])
+def test_gemm_shapes_and_tails(M, N, K, cta_pair):
     from tdm_b200 import ops
+    if cta_pair == 2 and M <= 128:
+        pytest.skip("a CTA pair needs more than one 128-row tile")
     a = _mk((M, K), seed=3)
     b = _mk((N, K), 0.05, seed=4)
     ref = a.float() @ b.float().t()
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, b, out_bf16=out)
+    ops.gemm(a, b, out_bf16=out, cta_pair=cta_pair)
     torch.cuda.synchronize()
     _close(out, ref, 6e-3, f"shape {M}x{N}x{K}")  # bf16 output rounding 2^-8
 
 
-def test_gemm_epilogue_full():
+@pytest.mark.parametrize("cta_pair", [1, 2])
+def test_gemm_epilogue_full(cta_pair):
     from tdm_b200 import ops
     B, T, N, K = 3, 200, 256, 192
     M = B * T
@@ -59,7 +67,7 @@ def test_gemm_epilogue_full():
     o32 = torch.empty(M, N, device="cuda")
     o16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, w, bias=bias, act=ops.ACT_GELU_TANH, pre_out=pre, gate=gate, rows_per_gate=T, res=res,
-             out_f32=o32, out_bf16=o16, alpha=0.5)
+             out_f32=o32, out_bf16=o16, alpha=0.5, cta_pair=cta_pair)
     torch.cuda.synchronize()
     v = 0.5 * (a.float() @ w.float().t()) + bias
     _close(pre, v, 6e-3, "pre_out")
@@ -87,7 +95,8 @@ def test_gemm_gelu_bwd_and_accumulate():
     _close(acc, ref, 2e-4, "accumulate")
 
 
-def test_gemm_lora_pair_and_segments():
+@pytest.mark.parametrize("cta_pair", [1, 2])
+def test_gemm_lora_pair_and_segments(cta_pair):
     from tdm_b200 import ops
     M, D, r = 300, 128, 64
     x = _mk((M, D), seed=10)
@@ -95,7 +104,7 @@ def test_gemm_lora_pair_and_segments():
     t = _mk((M, 3 * r), seed=12)            # x A^T for q,k,v
     bl = _mk((3 * D, r), 0.1, seed=13)      # stacked B_q;B_k;B_v
     out = torch.empty(M, 3 * D, device="cuda")
-    ops.gemm(x, w, a2=t, b2=bl, seg_n=D, seg_k2=r, out_f32=out)
+    ops.gemm(x, w, a2=t, b2=bl, seg_n=D, seg_k2=r, out_f32=out, cta_pair=cta_pair)
     torch.cuda.synchronize()
     ref = x.float() @ w.float().t()
     for s in range(3):
@@ -105,13 +114,14 @@ def test_gemm_lora_pair_and_segments():
     t2 = _mk((M, 16), seed=14)
     b2 = _mk((D, 16), 0.1, seed=15)
     out2 = torch.empty(M, D, device="cuda")
-    ops.gemm(x, w[:D], a2=t2, b2=b2, out_f32=out2)
+    ops.gemm(x, w[:D], a2=t2, b2=b2, out_f32=out2, cta_pair=cta_pair)
     torch.cuda.synchronize()
     _close(out2, x.float() @ w[:D].float().t() + t2.float() @ b2.float().t(), 2e-4, "rank-16 pair")
 
 
+@pytest.mark.parametrize("cta_pair", [1, 2])
 @pytest.mark.parametrize("split_k", [0, 3, 7])
-def test_gemm_split_k_accumulate(split_k):
+def test_gemm_split_k_accumulate(split_k, cta_pair):
     """wgrad-shaped contraction (few output tiles, long K): split-K partial sums are red.add'ed into out_f32."""
     from tdm_b200 import ops, _lib
     tokens, n_out, k_in = 4096, 192, 320
@@ -119,7 +129,7 @@ def test_gemm_split_k_accumulate(split_k):
     x = _mk((tokens, k_in), seed=21)
     acc = torch.randn(n_out, k_in, device="cuda")
     ref = acc + dy.float().t() @ x.float()
-    ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, res=acc, out_f32=acc, split_k=split_k)
+    ops.gemm(dy, x, a_mn_major=True, b_mn_major=True, res=acc, out_f32=acc, split_k=split_k, cta_pair=cta_pair, tile_n=128)
     torch.cuda.synchronize()
     _close(acc, ref, 3e-4, f"split_k={split_k}")
     with pytest.raises(_lib.TdmError):  # split-K is only defined for pure accumulation
