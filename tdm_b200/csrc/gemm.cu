@@ -320,12 +320,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // Warp-convergent: every lane polls the barriers and computes the (warp-uniform) descriptors, only the tcgen05
+    // instructions sit under elect.sync.  The compiler then keeps the operands in uniform registers; issuing from
+    // inside an `if (lane == 0)` region made it emit a register-broadcast loop per MMA (~30 SASS instructions,
+    // ~180 clocks) that capped the tensor pipe at ~54 % on 96-clock MMAs.
+    {
       const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u;  // bytes per UMMA_K=16 along K
-      const uint32_t b_kstep = p.b_mn ? 2048u : 32u;
+      const uint32_t a_kstep = (p.a_mn ? 2048u : 32u) >> 4;  // descriptor address units (16 B) per UMMA_K = 16
+      const uint32_t b_kstep = (p.b_mn ? 2048u : 32u) >> 4;
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u;
       const uint32_t b_lbo = p.b_mn ? 8192u : 16u;
+      const uint64_t a_desc0 = make_sdesc_sw128(smem_u32(smem), a_lbo, 1024);
+      const uint64_t b_desc0 = make_sdesc_sw128(smem_u32(smem) + Cfg::A_BYTES, b_lbo, 1024);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -340,23 +346,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + Cfg::A_BYTES;
+          if (elect_one()) {
+            const uint64_t da = a_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
+            const uint64_t db = b_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = make_sdesc_sw128(a_base + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_sdesc_sw128(b_base + k * b_kstep, b_lbo, 1024);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
 #ifndef TDM_DBG_NOMMA
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k != 0));
+              umma_bf16(tmem_d, da + uint64_t(k * a_kstep), db + uint64_t(k * b_kstep), idesc, (kb > kb0) || (k != 0));
 #endif
+            }
+            umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete
+        if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
