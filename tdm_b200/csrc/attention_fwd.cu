@@ -21,6 +21,7 @@ constexpr int CHUNK_BYTES = 128 * 128;  // one [128 rows x 64 bf16] swizzled chu
 struct AttnFwdParams {
   int B, H, Sq, Sk, d;
   int nd;         // ceil(d / 64) column chunks
+  int kv_stages;  // K / V ring depth (3 when it fits in shared memory, else 2)
   int dk16;       // ceil(d / 16) MMA k-steps for Q K^T
   float scale_log2;  // softmax scale * log2(e)
   const float* bias; // [B, Sk] additive, or null
@@ -36,12 +37,15 @@ __device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
   tmem_st8(taddr, r);
 }
 
-// TMEM map: S ping-pong at columns [0,128) and [128,256); O at [256, 256+pad16(d)).  P(j) (bf16, two keys per
+// Persistent kernel: one CTA per SM walks over (query tile, head, batch) work items; the K/V ring, the S ping-pong
+// and every barrier phase run continuously across items, Q is double-buffered and the next item's Q / first K,V
+// tiles are in flight while the current item finishes, so the per-item fixed cost (barrier set-up, TMEM allocation,
+// descriptor fetch, first-load latency -- ~5 us of a 17 us CTA in the one-tile-per-CTA version) is paid once per SM.
+// TMEM map: S ping-pong at columns [0,128) and [128,256); O at [256, 256+pad16(d)).  P(g) (bf16, two keys per
 // 32-bit column) overwrites columns [0,64) of the S buffer it was computed from and is the A operand of the
 // P V contraction directly from tensor memory: P never touches shared memory.
 // Two softmax warpgroups share every 128-query tile: warps 0-3 own keys [0,64) of the tile, warps 4-7 keys
-// [64,128) (thread == query row in both), so each SM sub-partition always has two warps to hide the
-// TMEM / MUFU / shared-memory latencies of the other; they exchange row maxima through shared memory.
+// [64,128) (thread == query row in both); they exchange row maxima through shared memory.
 constexpr int FWD_THREADS = 320;  // 8 softmax warps + TMA warp + MMA warp
 
 __global__ void __launch_bounds__(FWD_THREADS, 1)
@@ -50,35 +54,48 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int tile_bytes = p.nd * CHUNK_BYTES;
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + tile_bytes;           // 2 stages
-  uint8_t* sV = sK + 2 * tile_bytes;       // 2 stages
-  float* sBias = reinterpret_cast<float*>(sV + 2 * tile_bytes);  // 2 x 128 floats
+  const int KS = p.kv_stages;
+  uint8_t* sQ = smem;                      // 2 stages
+  uint8_t* sK = sQ + 2 * tile_bytes;       // KS stages
+  uint8_t* sV = sK + KS * tile_bytes;      // KS stages
+  float* sBias = reinterpret_cast<float*>(sV + KS * tile_bytes);  // 2 x 128 floats
   float* sMax = sBias + 256;                                      // [2 tiles][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 512);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* kv_empty = bars + 5;  // [2]
-  uint64_t* s_full = bars + 7;    // [2]
-  uint64_t* p_full = bars + 9;
-  uint64_t* pv_done = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  float* sL = sMax + 512;                                         // [2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sL + 256);
+  uint64_t* q_full = bars;        // [2]
+  uint64_t* q_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;    // [2]
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint64_t* o_free = bars + 8;
+  uint64_t* k_full = bars + 9;    // [3]
+  uint64_t* v_full = bars + 12;   // [3]
+  uint64_t* k_empty = bars + 15;  // [3]  K stage free as soon as Q K^T of the tile retired (a whole tile earlier than V)
+  uint64_t* v_empty = bars + 18;  // [3]  V stage free: P V of the tile retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * ATT_BM, h = blockIdx.y, b = blockIdx.z;
   const int n_kv = (p.Sk + ATT_BN - 1) / ATT_BN;
+  const int n_qt = (p.Sq + ATT_BM - 1) / ATT_BM;
+  const int n_items = n_qt * p.H * p.B;
+  const int my_items = ((int)blockIdx.x < n_items) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total_tiles = my_items * n_kv;
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&k_empty[i], 1);
     }
     mbar_init(p_full, 256);
     mbar_init(pv_done, 1);
+    mbar_init(o_free, 256);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -95,66 +112,80 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
       tma_prefetch_desc(&tmV);
-      mbar_arrive_expect_tx(q_full, tile_bytes);
-      for (int c = 0; c < p.nd; ++c) tma_load_4d(sQ + c * CHUNK_BYTES, &tmQ, q_full, c * 64, q0, h, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1;
-        mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], tile_bytes);
-        for (int c = 0; c < p.nd; ++c)
-          tma_load_4d(sK + st * tile_bytes + c * CHUNK_BYTES, &tmK, &k_full[st], c * 64, j * ATT_BN, h, b);
-        mbar_arrive_expect_tx(&v_full[st], tile_bytes);
-        for (int c = 0; c < p.nd; ++c)
-          tma_load_4d(sV + st * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[st], c * 64, j * ATT_BN, h, b);
+      int g = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int q0 = (item % n_qt) * ATT_BM, h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
+        const int qs = it & 1;
+        mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qs], tile_bytes);
+        for (int c = 0; c < p.nd; ++c) tma_load_4d(sQ + qs * tile_bytes + c * CHUNK_BYTES, &tmQ, &q_full[qs], c * 64, q0, h, b);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const int st = g % KS;
+          const uint32_t ph = (uint32_t)(g / KS) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], tile_bytes);
+          for (int c = 0; c < p.nd; ++c)
+            tma_load_4d(sK + st * tile_bytes + c * CHUNK_BYTES, &tmK, &k_full[st], c * 64, j * ATT_BN, h, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], tile_bytes);
+          for (int c = 0; c < p.nd; ++c)
+            tma_load_4d(sV + st * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[st], c * 64, j * ATT_BN, h, b);
+        }
       }
     }
   } else if (warp == 9) {
     // ===================== MMA issuer =====================
-    // The whole warp stays convergent (every lane polls the barriers, every lane computes the -- warp-uniform --
-    // descriptors) and only the tcgen05 instructions sit under elect.sync: the compiler keeps the operands in
-    // uniform registers instead of emitting a broadcast loop per MMA, which matters because one attention tile
-    // is 13 small MMAs (40-64 tensor-pipe clocks each) and their issue cost was the kernel's bottleneck.
+    // Warp-convergent (every lane polls and computes the warp-uniform descriptors), tcgen05 ops under elect.sync:
+    // operands stay in uniform registers.  The tile stream is flat across items: S(g+1) = Q K^T of the NEXT tile --
+    // possibly the next item's first -- is issued before P(g) V(g), so the tensor pipe never drains between items.
     const uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(128, p.dk16 * 16, 0, 1);  // A = P from TMEM; B = V MN-major (d contiguous)
-    const uint64_t q_desc = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+    const uint64_t q_desc0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
     const uint64_t k_desc0 = make_sdesc_sw128(smem_u32(sK), 16, 1024);
     const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
     const uint32_t stage_step = uint32_t(tile_bytes) >> 4;  // descriptor address field counts 16-byte units
     const int dk16 = p.dk16;
-    auto issue_qk = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&k_full[st], (j >> 1) & 1);
+    auto issue_qk = [&](int g) {
+      const int it = g / n_kv, j = g - it * n_kv;
+      const int st = g % KS;
+      if (j == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
+      mbar_wait(&k_full[st], (uint32_t)(g / KS) & 1);
       tc_fence_after();
       if (elect_one()) {
+        const uint64_t qd = q_desc0 + uint64_t((it & 1) * stage_step);
         const uint64_t kd = k_desc0 + uint64_t(st * stage_step);
-        const uint32_t sd = tmem_S + (j & 1) * 128;
+        const uint32_t sd = tmem_S + (g & 1) * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (k < dk16) {
+          if (k < dk16) {  // 16 head-dim columns per step: four steps per 64-column chunk
             const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
-            umma_bf16(sd, q_desc + off, kd + off, idesc_qk, k != 0);
+            umma_bf16(sd, qd + off, kd + off, idesc_qk, k != 0);
           }
         }
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[g & 1]);
+        umma_commit(&k_empty[st]);
+        if (j == n_kv - 1) umma_commit(&q_empty[it & 1]);  // last read of this item's Q tile
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
-    issue_qk(0);
-    for (int j = 0; j < n_kv; ++j) {
-      // S((j+1)&1) still holds P(j-1): tcgen05.mma executes in issue order, so this S write follows P V (j-1)
-      if (j + 1 < n_kv) issue_qk(j + 1);
-      const int st = j & 1;
-      mbar_wait(p_full, j & 1);
-      mbar_wait(&v_full[st], (j >> 1) & 1);
+    if (total_tiles > 0) issue_qk(0);
+    for (int g = 0; g < total_tiles; ++g) {
+      // S((g+1)&1) still holds P(g-1): tcgen05.mma executes in issue order, so this S write follows P V (g-1)
+      if (g + 1 < total_tiles) issue_qk(g + 1);
+      const int it = g / n_kv, j = g - it * n_kv;
+      const int st = g % KS;
+      mbar_wait(p_full, g & 1);
+      mbar_wait(&v_full[st], (uint32_t)(g / KS) & 1);
+      if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);  // the previous item's epilogue has read O
       tc_fence_after();
       if (elect_one()) {
         const uint64_t vd = v_desc0 + uint64_t(st * stage_step);
-        const uint32_t p_addr = tmem_S + (j & 1) * 128;
+        const uint32_t p_addr = tmem_S + (g & 1) * 128;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)  // 16 keys = 8 packed TMEM columns = 2048 smem bytes per step
           umma_bf16_ts(tmem_O, p_addr + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0);
-        umma_commit(&kv_empty[st]);
+        umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
       __syncwarp();
@@ -168,141 +199,143 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // O columns this half rescales / writes out (8-column groups split between the two warpgroups)
     const int og = (p.d + 7) / 8;
     const int oc0 = wg == 0 ? 0 : ((og + 1) / 2) * 8, oc1 = wg == 0 ? ((og + 1) / 2) * 8 : p.d;
-    float m_used = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < n_kv; ++j) {
-      const int buf = j & 1;
-      const bool need_bias = p.bias != nullptr || (j + 1) * ATT_BN > p.Sk;  // CTA-uniform
-      if (need_bias) {  // additive key bias (pre-multiplied by log2 e) and the key-padding mask of a ragged last tile
-        if (wg == 0) {
-          const int kv = j * ATT_BN + row;
-          float bv = 0.f;
-          if (kv >= p.Sk) bv = -INFINITY;
-          else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
-          sBias[buf * 128 + row] = bv;
+    int g = 0;
+    for (int it = 0; it < my_items; ++it) {
+      const int item = (int)blockIdx.x + it * (int)gridDim.x;
+      const int q0 = (item % n_qt) * ATT_BM, h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++g) {
+        const int buf = g & 1;
+        const bool need_bias = p.bias != nullptr || (j + 1) * ATT_BN > p.Sk;  // CTA-uniform
+        if (need_bias) {  // additive key bias (pre-multiplied by log2 e) and the key-padding mask of a ragged last tile
+          if (wg == 0) {
+            const int kv = j * ATT_BN + row;
+            float bv = 0.f;
+            if (kv >= p.Sk) bv = -INFINITY;
+            else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
+            sBias[buf * 128 + row] = bv;
+          }
+          asm volatile("bar.sync 2, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-      }
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
-      uint32_t sr[64];
-#ifdef TDM_DBG_NOLD
-#pragma unroll
-      for (int i = 0; i < 64; ++i) sr[i] = __float_as_uint(0.001f * (float)(i + row));
-#else
-      tmem_ld32(s_addr + wg * 64, sr);
-      tmem_ld32(s_addr + wg * 64 + 32, sr + 32);
-      tmem_ld_wait();
-#endif
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-      if (need_bias) {
-        const float* bias_s = sBias + buf * 128 + wg * 64;
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias_s + i);
-          const float v0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, bb.x), v1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, bb.y);
-          const float v2 = fmaf(__uint_as_float(sr[i + 2]), p.scale_log2, bb.z), v3 = fmaf(__uint_as_float(sr[i + 3]), p.scale_log2, bb.w);
-          sr[i] = __float_as_uint(v0); sr[i + 1] = __float_as_uint(v1); sr[i + 2] = __float_as_uint(v2); sr[i + 3] = __float_as_uint(v3);
-          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; i += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sr[i])); mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
-        }
-      }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (!need_bias) mx *= p.scale_log2;  // scale > 0
-      // exchange the half-row maxima (double-buffered by tile parity: one barrier per tile is enough)
-      float* mx_s = sMax + buf * 256;
-      mx_s[wg * 128 + row] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, mx_s[(wg ^ 1) * 128 + row]);
-      // Lazy rescale: O and l keep the stale maximum until it is exceeded by more than 2^8 (exact after the final
-      // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform (tcgen05.ld/st are collective) and
-      // identical in both warpgroups, which see the same rows and the same exchanged maxima.
-      const float m_new = fmaxf(m_used, mx);
-      if (j == 0) {
-        m_used = m_new;
-      } else if (__any_sync(0xffffffffu, m_new - m_used > 8.f)) {
-        mbar_wait(pv_done, (j - 1) & 1);  // O must not be rescaled under an in-flight P V
+        mbar_wait(&s_full[buf], (g >> 1) & 1);
         tc_fence_after();
-        const float alpha = ex2_fast(m_used - m_new);
-        l_run *= alpha;
-        m_used = m_new;
-        for (int c = oc0; c < oc1; c += 8) {
+        const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
+        uint32_t sr[64];
+        tmem_ld32(s_addr + wg * 64, sr);
+        tmem_ld32(s_addr + wg * 64 + 32, sr + 32);
+        tmem_ld_wait();
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if (need_bias) {
+          const float* bias_s = sBias + buf * 128 + wg * 64;
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            const float4 bb = *reinterpret_cast<const float4*>(bias_s + i);
+            const float v0 = fmaf(__uint_as_float(sr[i]), p.scale_log2, bb.x), v1 = fmaf(__uint_as_float(sr[i + 1]), p.scale_log2, bb.y);
+            const float v2 = fmaf(__uint_as_float(sr[i + 2]), p.scale_log2, bb.z), v3 = fmaf(__uint_as_float(sr[i + 3]), p.scale_log2, bb.w);
+            sr[i] = __float_as_uint(v0); sr[i + 1] = __float_as_uint(v1); sr[i + 2] = __float_as_uint(v2); sr[i + 3] = __float_as_uint(v3);
+            mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 4) {
+            mx0 = fmaxf(mx0, __uint_as_float(sr[i])); mx1 = fmaxf(mx1, __uint_as_float(sr[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(sr[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
+          }
+        }
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        if (!need_bias) mx *= p.scale_log2;  // scale > 0
+        // exchange the half-row maxima (double-buffered by tile parity: one barrier per tile is enough)
+        float* mx_s = sMax + buf * 256;
+        mx_s[wg * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mx = fmaxf(mx, mx_s[(wg ^ 1) * 128 + row]);
+        // Lazy rescale: O and l keep the stale maximum until it is exceeded by more than 2^8 (exact after the final
+        // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform (tcgen05.ld/st are collective) and
+        // identical in both warpgroups, which see the same rows and the same exchanged maxima.
+        const float m_new = fmaxf(m_used, mx);
+        if (j == 0) {
+          m_used = m_new;
+        } else if (__any_sync(0xffffffffu, m_new - m_used > 8.f)) {
+          mbar_wait(pv_done, (g - 1) & 1);  // O must not be rescaled under an in-flight P V
+          tc_fence_after();
+          const float alpha = ex2_fast(m_used - m_new);
+          l_run *= alpha;
+          m_used = m_new;
+          for (int c = oc0; c < oc1; c += 8) {
+            uint32_t r[8];
+            tmem_ld8(tmem_O + lane_off + c, r);
+            tmem_ld_wait();
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * alpha;
+            tmem_st8w(tmem_O + lane_off + c, v);
+          }
+          tmem_st_wait();
+        }
+        // P is packed in place: sr[i] <- bf16x2(p[2i], p[2i+1]) (the write index never passes the read index)
+        float l0 = 0.f, l1 = 0.f;
+        if (need_bias) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2_fast(__uint_as_float(sr[2 * i]) - m_used);
+            const float p1 = ex2_fast(__uint_as_float(sr[2 * i + 1]) - m_used);
+            l0 += p0;
+            l1 += p1;
+            sr[i] = pack_bf16(p0, p1);
+          }
+        } else {
+          const float nm = -m_used;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
+            const float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
+            l0 += p0;
+            l1 += p1;
+            sr[i] = pack_bf16(p0, p1);
+          }
+        }
+        l_run += l0 + l1;
+        tmem_st32(s_addr + wg * 32, sr);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(p_full);
+      }
+      // combine the two halves' row sums (sL is only touched here: the barrier pair orders it against the last item)
+      sL[wg * 128 + row] = l_run;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      l_run += sL[(wg ^ 1) * 128 + row];
+      mbar_wait(pv_done, (g - 1) & 1);
+      tc_fence_after();
+      const int q = q0 + row;
+      const float inv_l = 1.f / l_run;
+      if (q < p.Sq && wg == 0) {
+        if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_used + log2f(l_run)) * 0.6931471805599453f;
+      }
+      bf16* orow = p.O + (long)b * p.o_stride_b + (long)q * p.o_stride_s + (long)h * p.o_stride_h;
+      uint4 w[8];  // at most 8 eight-column groups per half (d <= 128); fully unrolled so it stays in registers
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = oc0 + 8 * i;
+        if (c < oc1) {  // warpgroup-uniform
           uint32_t r[8];
           tmem_ld8(tmem_O + lane_off + c, r);
           tmem_ld_wait();
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]) * alpha;
-          tmem_st8w(tmem_O + lane_off + c, v);
-        }
-        tmem_st_wait();
-      }
-      // P is packed in place: sr[i] <- bf16x2(p[2i], p[2i+1]) (the write index never passes the read index)
-      float l0 = 0.f, l1 = 0.f;
-      if (need_bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float p0 = ex2_fast(__uint_as_float(sr[2 * i]) - m_used);
-          const float p1 = ex2_fast(__uint_as_float(sr[2 * i + 1]) - m_used);
-          l0 += p0;
-          l1 += p1;
-          sr[i] = pack_bf16(p0, p1);
-        }
-      } else {
-        const float nm = -m_used;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-#ifdef TDM_DBG_NOEXP
-          const float p0 = fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm);
-          const float p1 = fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm);
-#else
-          const float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
-          const float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
-#endif
-          l0 += p0;
-          l1 += p1;
-          sr[i] = pack_bf16(p0, p1);
+          w[i].x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
+          w[i].y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
+          w[i].z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
+          w[i].w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
         }
       }
-      l_run += l0 + l1;
-#ifndef TDM_DBG_NOST
-      tmem_st32(s_addr + wg * 32, sr);
-      tmem_st_wait();
-#endif
       tc_fence_before();
-      mbar_arrive(p_full);
-    }
-    // combine the two halves' row sums
-    float* l_s = sMax;  // free now: every thread is past the last exchange barrier... of the previous tile at least
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l_s[wg * 128 + row] = l_run;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    l_run += l_s[(wg ^ 1) * 128 + row];
-    mbar_wait(pv_done, (n_kv - 1) & 1);
-    tc_fence_after();
-    const int q = q0 + row;
-    const float inv_l = 1.f / l_run;
-    if (q < p.Sq && wg == 0) {
-      if (p.lse) p.lse[((long)b * p.H + h) * p.Sq + q] = (m_used + log2f(l_run)) * 0.6931471805599453f;
-    }
-    bf16* orow = p.O + (long)b * p.o_stride_b + (long)q * p.o_stride_s + (long)h * p.o_stride_h;
-    for (int c = oc0; c < oc1; c += 8) {
-      uint32_t r[8];
-      tmem_ld8(tmem_O + lane_off + c, r);
-      tmem_ld_wait();
+      mbar_arrive(o_free);  // O is in registers: the next item's first P V may overwrite it
       if (q < p.Sq) {
-        uint4 w;
-        w.x = pack_bf16(__uint_as_float(r[0]) * inv_l, __uint_as_float(r[1]) * inv_l);
-        w.y = pack_bf16(__uint_as_float(r[2]) * inv_l, __uint_as_float(r[3]) * inv_l);
-        w.z = pack_bf16(__uint_as_float(r[4]) * inv_l, __uint_as_float(r[5]) * inv_l);
-        w.w = pack_bf16(__uint_as_float(r[6]) * inv_l, __uint_as_float(r[7]) * inv_l);
-        *reinterpret_cast<uint4*>(orow + c) = w;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = oc0 + 8 * i;
+          if (c < oc1) *reinterpret_cast<uint4*>(orow + c) = w[i];
+        }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // sL reads done before the next item's write
     }
   }
   tc_fence_before();
@@ -348,13 +381,16 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   p.bias = a->bias;
   p.O = (bf16*)a->O; p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.lse = a->lse;
-  const int smem = 5 * p.nd * CHUNK_BYTES + 1024 + 2048 + 256 + 1024;
+  const int extra = 1024 + 2048 + 1024 + 512 + 1024;
+  p.kv_stages = (8 * p.nd * CHUNK_BYTES + extra <= 232448) ? 3 : 2;  // head_dim <= 64: 16 KB tiles, three stages fit
+  const int smem = (2 + 2 * p.kv_stages) * p.nd * CHUNK_BYTES + extra;
   static int smem_set = 0;
   if (smem > smem_set) {
     TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     smem_set = smem;
   }
-  dim3 grid((a->Sq + ATT_BM - 1) / ATT_BM, a->H, a->B);
+  const long items = (long)((a->Sq + ATT_BM - 1) / ATT_BM) * a->H * a->B;
+  const int grid = (int)(items < num_sms() ? items : num_sms());
   ::tdm::count_launch(); attn_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;

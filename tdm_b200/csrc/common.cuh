@@ -333,6 +333,18 @@ __device__ __forceinline__ uint64_t make_sdesc_sw128(uint32_t smem_addr, uint32_
   return d;
 }
 
+// Same descriptor for the 64-byte swizzle (rows of 32 bf16; layout type 4): used where 128-byte rows would waste
+// shared memory (attention tiles of head_dim 72 = three 32-column chunks instead of two 64-column ones).
+__device__ __forceinline__ uint64_t make_sdesc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFF) >> 4);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(4) << 61;
+  return d;
+}
+
 // ---- small math --------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
