@@ -235,6 +235,10 @@ int tdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_coef,
                    void* stream);
 
+/* EMAModel.step (diffusers; reference main.py:188-189, 553-554) on a flat fp32 arena:
+ * shadow -= (1 - decay) * (shadow - param). */
+int tdm_ema_update(float* shadow, const float* param, int64_t n, float decay, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * One PixArt DiT block (diffusers BasicTransformerBlock, norm_type="ada_norm_single"; SURVEY.md
  * Appendix A) forward and backward as ONE call each: the library sequences its own kernels

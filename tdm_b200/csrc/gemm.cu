@@ -747,7 +747,8 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   int bn = g->tile_n;
   int pair = g->cta_pair;  // 0 choose, 1 single CTA, 2 CTA pair
   TDM_REQUIRE(pair >= 0 && pair <= 2, "tdm_gemm_bf16: cta_pair must be 0 (choose), 1 (single) or 2 (pair)");
-  if (pair == 0) pair = (g->K >= 4096 && g->M >= 2048 && g->N >= 2048 && !g->a_mn_major && !g->b_mn_major) ? 2 : 1;
+  if (pair == 0)  // measured (profiles/r01_kernel_microbench): FF2 8192x1152x4608 82 vs 91 us, 8192^3 753 vs 964 us
+    pair = (g->M >= 1024 && (g->K >= 2048 || g->N >= 4096) && !g->a_mn_major && !g->b_mn_major && g->seg_n == 0) ? 2 : 1;
   auto cost = [&](int b, bool pr) {
     const long mt = pr ? (g->M + 255) / 256 : (g->M + 127) / 128;
     const long t = mt * ((g->N + b - 1) / b);

@@ -149,6 +149,22 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// EMA of the student parameters (diffusers EMAModel.step, reference main.py:553-554): shadow -= (1 - decay) * (shadow - p)
+__global__ void ema_kernel(float* __restrict__ shadow, const float* __restrict__ p, long n, float one_minus_decay) {
+  const long n4 = n >> 2;
+  float4* s4 = reinterpret_cast<float4*>(shadow);
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 a = s4[i];
+    const float4 b = p4[i];
+    a.x -= one_minus_decay * (a.x - b.x);
+    a.y -= one_minus_decay * (a.y - b.y);
+    a.z -= one_minus_decay * (a.z - b.z);
+    a.w -= one_minus_decay * (a.w - b.w);
+    s4[i] = a;
+  }
+}
+
 }  // namespace tdm
 
 using namespace tdm;
@@ -216,6 +232,14 @@ extern "C" int tdm_adamw_step(float* param, const float* grad, float* exp_avg, f
   ::tdm::count_launch(); adamw_kernel<<<ts_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (bf16*)param_bf16,
                                                                      (long)n, lr, beta1, beta2, eps, weight_decay, bc1,
                                                                      bc2_sqrt, grad_coef);
+  TDM_CHECK_CUDA(cudaGetLastError());
+  return TDM_OK;
+}
+
+extern "C" int tdm_ema_update(float* shadow, const float* param, int64_t n, float decay, void* stream) {
+  TDM_REQUIRE(shadow && param && n > 0 && n % 4 == 0, "tdm_ema_update: bad input");
+  TDM_REQUIRE((((uintptr_t)shadow | (uintptr_t)param) & 15) == 0, "tdm_ema_update: buffers must be 16-byte aligned");
+  ::tdm::count_launch(); ema_kernel<<<ts_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(shadow, param, (long)n, 1.f - decay);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

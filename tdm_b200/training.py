@@ -109,6 +109,42 @@ class FlatAdamW:
             g.zero_()
 
 
+class EMAModel:
+    """diffusers.training_utils.EMAModel as the reference uses it (main.py:188-189 ctor, 325-326 .to(device),
+    553-554 .step(unet.parameters())): an exponential moving average of the student's trainable parameters, kept as
+    one flat fp32 shadow per arena and updated by one kernel launch.  Decay schedule of EMAModel without warm-up:
+    min(decay, (1 + step) / (10 + step))."""
+
+    def __init__(self, model, decay=0.9999, min_decay=0.0):
+        self.model, self.decay, self.min_decay = model, decay, min_decay
+        self.optimization_step = 0
+        self.shadow = [p.detach().clone() for p in model.flat_params()]
+
+    def get_decay(self, optimization_step):
+        step = max(0, optimization_step - 1)
+        if step <= 0:
+            return 0.0
+        return max(self.min_decay, min(self.decay, (1 + step) / (10 + step)))
+
+    def step(self, parameters=None):
+        from ._lib import check, ptr, stream_handle, lib
+        self.optimization_step += 1
+        d = self.get_decay(self.optimization_step)
+        for sh, p in zip(self.shadow, self.model.flat_params()):
+            check(lib().tdm_ema_update(ptr(sh), ptr(p), p.numel(), float(d), stream_handle()))
+
+    def copy_to(self, model):
+        with torch.no_grad():
+            for sh, p in zip(self.shadow, model.flat_params()):
+                p.copy_(sh)
+        model.mark_updated()
+        model._flat16_version = model._lflat16_version = -1
+
+    def to(self, device=None, dtype=None):
+        self.shadow = [s.to(device=device) for s in self.shadow]
+        return self
+
+
 # ----------------------------------------------------------------------------------------------------
 # the repaired iteration
 # ----------------------------------------------------------------------------------------------------

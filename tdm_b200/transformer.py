@@ -281,6 +281,9 @@ class Transformer2DModel(nn.Module):
         self.lora_targets = tuple(targets)
         self.lora_r = rank
         self.lora_scale = float(alpha if alpha is not None else rank) / rank
+        import types
+        self.peft_config = {"default": types.SimpleNamespace(r=rank, lora_alpha=float(alpha if alpha is not None else rank),
+                                                              target_modules=list(targets))}
         self._lflat = torch.zeros(L.size, device=self.device, dtype=torch.float32)
         gen = torch.Generator(device="cpu")
         gen.manual_seed(seed if seed is not None else torch.initial_seed() % (2 ** 63))
@@ -299,6 +302,13 @@ class Transformer2DModel(nn.Module):
         self._lflat16 = self._lgrad = None
         self._flat16_eff = self._eff_key = self._merged_structs = None
         return self
+
+    def peft_state_dict(self, adapter_name="default"):
+        """What peft.get_peft_model_state_dict returns for a wrapped model: adapter weights only, keys prefixed with
+        `base_model.model.` and with the adapter name dropped (`...to_q.lora_A.weight`)."""
+        tag = f".{adapter_name}.weight"
+        return {"base_model.model." + n[:-len(tag)] + ".weight": p.detach()
+                for n, p in self.named_parameters() if ".lora_" in n and n.endswith(tag)}
 
     def lora_parameters(self):
         return [p for n, p in self.named_parameters() if ".lora_" in n]

@@ -28,3 +28,24 @@ def append_dims(x, target_dims):
     if dims_to_append < 0:
         raise ValueError(f"input has {x.ndim} dims but target_dims is {target_dims}, which is less")
     return x[(...,) + (None,) * dims_to_append]
+
+
+def get_module_kohya_state_dict(module, prefix: str, dtype: torch.dtype, adapter_name: str = "default"):
+    """utils.py:76-93: LoRA weights in the kohya-ss naming that `pipe.load_lora_weights` consumes (README.md:49, 96, 119):
+    `base_model.model` -> prefix, lora_A -> lora_down, lora_B -> lora_up, every dot but the last two -> underscore, plus
+    one `.alpha` entry per adapted linear.  `module` is a tdm_b200 Transformer2DModel with add_lora() applied (it
+    exposes `peft_state_dict()` / `peft_config` the way a peft-wrapped model would through get_peft_model_state_dict)."""
+    kohya_ss_state_dict = {}
+    for peft_key, weight in module.peft_state_dict(adapter_name=adapter_name).items():
+        if "base_model.model" in peft_key:
+            kohya_key = peft_key.replace("base_model.model", prefix)
+        else:
+            kohya_key = prefix + "." + peft_key
+        kohya_key = kohya_key.replace("lora_A", "lora_down")
+        kohya_key = kohya_key.replace("lora_B", "lora_up")
+        kohya_key = kohya_key.replace(".", "_", kohya_key.count(".") - 2)
+        kohya_ss_state_dict[kohya_key] = weight.to(dtype)
+        if "lora_down" in kohya_key:
+            alpha_key = f'{kohya_key.split(".")[0]}.alpha'
+            kohya_ss_state_dict[alpha_key] = torch.tensor(module.peft_config[adapter_name].lora_alpha).to(dtype)
+    return kohya_ss_state_dict
