@@ -134,6 +134,9 @@ if __name__ == "__main__":
     if "wgrad" in which:
         wgrad_case("w_o", M, D, D)
         wgrad_case("w_o_nosplit", M, D, D, 1)
+        wgrad_case("w_o_split2", M, D, D, 2)
+        wgrad_case("w_o_split3", M, D, D, 3)
+        wgrad_case("w_qkv_split2", M, 3 * D, D, 2)
         wgrad_case("w_qkv", M, 3 * D, D)
         wgrad_case("w_ff1", M, 4 * D, D)
         wgrad_case("w_ff2", M, D, 4 * D)

@@ -120,11 +120,13 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CU
     tmem_ld32(taddr + c, acc);
     tmem_ld_wait();
     if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
-      if (row_ok) {
+      if (row_ok) {  // 16-byte vector reds: N % 8 == 0 and ld_out_f32 % 4 == 0 keep every group aligned and in range
         float* o = p.out_f32 + (long)m * p.ld_out_f32 + n0 + c;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (n0 + c + i < p.N) atomicAdd(o + i, p.alpha * __uint_as_float(acc[i]));
+        for (int i = 0; i < 32; i += 4)
+          if (n0 + c + i < p.N)
+            red_add_v4(o + i, p.alpha * __uint_as_float(acc[i]), p.alpha * __uint_as_float(acc[i + 1]),
+                       p.alpha * __uint_as_float(acc[i + 2]), p.alpha * __uint_as_float(acc[i + 3]));
       }
       continue;
     }
@@ -678,9 +680,9 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
     const int tiles0 = p.num_m_tiles * p.num_n_tiles;
     const int nk = (p.K + BK - 1) / BK;
     int want = g->split_k;
-    if (want == 0 && acc_only && tiles0 * 4 <= num_sms() && nk >= 16) {  // only when the output is a handful of tiles
-      want = (2 * num_sms() + tiles0 - 1) / tiles0;  // ~2 work units per SM
-      if (want > nk / 4) want = nk / 4;              // keep >= 4 k-blocks per unit
+    if (want == 0 && acc_only && tiles0 < num_sms() && nk >= 16) {  // the output tiles alone cannot fill the machine
+      want = (num_sms() + tiles0 / 2) / tiles0;  // ~1 work unit per SM (1152x1152 wgrad: 54 tiles x 3 -> 39 vs 54 us)
+      if (want > nk / 8) want = nk / 8;          // keep >= 8 k-blocks per unit: fewer partial sums to reduce in HBM
     }
     if (want > 1) {
       if (!acc_only) return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: split_k needs an accumulate-only epilogue (res == out_f32)");
@@ -724,6 +726,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   TDM_REQUIRE(g->N % 8 == 0, "tdm_gemm_bf16: N=%d must be a multiple of 8", g->N);
   TDM_REQUIRE(g->lda % 8 == 0 && g->ldb % 8 == 0, "tdm_gemm_bf16: lda/ldb must be multiples of 8");
   TDM_REQUIRE(((uintptr_t)g->A & 15) == 0 && ((uintptr_t)g->B & 15) == 0, "tdm_gemm_bf16: A/B must be 16-byte aligned");
+  TDM_REQUIRE((((uintptr_t)g->out_f32 | (uintptr_t)g->out_bf16) & 15) == 0, "tdm_gemm_bf16: outputs must be 16-byte aligned");
   TDM_REQUIRE(g->act >= TDM_ACT_NONE && g->act <= TDM_ACT_SILU_BWD, "tdm_gemm_bf16: unknown act %d", g->act);
   TDM_REQUIRE((g->act != TDM_ACT_GELU_TANH_BWD && g->act != TDM_ACT_SILU_BWD) || g->act_in,
               "tdm_gemm_bf16: backward activations need act_in");
