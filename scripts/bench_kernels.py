@@ -103,8 +103,31 @@ def ln_case(M, D):
     print(json.dumps({"kernel": "ln_modulate_bwd", "M": M, "D": D, "us": round(us, 2), "gbs": round(M * D * 16 / us / 1e3, 1)}), flush=True)
 
 
+def solver_case(B):
+    """Solver step / re-noise / loss at the real batch and at a large synthetic batch (HBM bandwidth visible)."""
+    from tdm_b200.scheduler import DDPMScheduler
+    sch = DDPMScheduler(beta_start=1e-4, beta_end=0.02, beta_schedule="linear", steps_offset=1, clip_sample=False)
+    a = torch.sqrt(sch.alphas_cumprod).to(DEV).bfloat16()
+    sg = torch.sqrt(1 - sch.alphas_cumprod).to(DEV).bfloat16()
+    acp = sch.alphas_cumprod.to(DEV).float().contiguous()
+    out = [torch.randn(B, 8, 64, 64, device=DEV) for _ in range(NB)]
+    x = [torch.randn(B, 4, 64, 64, device=DEV).bfloat16() for _ in range(NB)]
+    t = torch.randint(1, 1000, (B,), device=DEV)
+    n = B * 4 * 64 * 64
+    us = timeit(lambda i: ops.solver_step(out[i % NB], x[i % NB], t, a, sg, "epsilon", t_next=t - 1, alphas_cumprod=acp,
+                                          next_dtype=torch.bfloat16, want_eps=False))
+    print(json.dumps({"kernel": "solver_step", "B": B, "us": round(us, 2), "gbs": round(n * (4 + 2 + 4 + 2) / us / 1e3, 1)}), flush=True)
+    nz = [torch.randn(B, 4, 64, 64, device=DEV).bfloat16() for _ in range(NB)]
+    t2 = torch.clamp(t + 50, max=999)
+    us = timeit(lambda i: ops.renoise(x[i % NB], nz[i % NB], t, t2, a, sg, torch.bfloat16))
+    print(json.dumps({"kernel": "renoise", "B": B, "us": round(us, 2), "gbs": round(n * 6 / us / 1e3, 1)}), flush=True)
+    m = [torch.randn(B, 4, 64, 64, device=DEV) for _ in range(3)]
+    us = timeit(lambda i: ops.tdm_loss(m[0], m[1], m[2], 4.5, True))
+    print(json.dumps({"kernel": "tdm_loss_fwd_bwd", "B": B, "us": round(us, 2), "gbs": round(n * (3 * 4 * 2 + 4) / us / 1e3, 1)}), flush=True)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gemm", "wgrad", "attn", "ln"]
+    which = sys.argv[1:] or ["gemm", "wgrad", "attn", "ln", "solver"]
     M, D = 8192, 1152
     if "pair" in which:
         for nm, (m, n, k), epi in (("qkv", (M, 3 * D, D), "bias"), ("q2", (M, D, D), "bias"), ("o_proj", (M, D, D), "gate_res_2out"),
@@ -151,3 +174,7 @@ if __name__ == "__main__":
         attn_case("cross", 8, 16, 1024, 120, 72, bwd=True, bias=True)
     if "ln" in which:
         ln_case(M, D)
+    if "solver" in which:
+        solver_case(8)
+        solver_case(64)
+        solver_case(2048)

@@ -48,6 +48,39 @@ __device__ __forceinline__ void wr_dt(void* p, long i, float v, int dt) {
 }
 __device__ __forceinline__ long wrap_index(long t, int len) { return t < 0 ? t + len : t; }  // python indexing
 
+// 128-bit (fp32) / 64-bit (fp16, bf16) vector access to 4 consecutive elements; i % 4 == 0 and 16-byte aligned bases.
+__device__ __forceinline__ void ld4_dt(const void* p, long i, int dt, float* o) {
+  if (dt == TDM_F32) {
+    const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  } else {
+    const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(p) + i);
+    if (dt == TDM_F16) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    } else {
+      const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y);
+      o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+  }
+}
+__device__ __forceinline__ void st4_dt(void* p, long i, int dt, const float* v) {
+  if (dt == TDM_F32) {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + i) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (dt == TDM_F16) {
+    __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&a);
+    w.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + i) = w;
+  } else {
+    uint2 w;
+    w.x = pack_bf16(v[0], v[1]);
+    w.y = pack_bf16(v[2], v[3]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(p) + i) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // solver step: eps-half select + CFG combine + predicted_origin + scheduler.add_noise + low-p cast
 // ------------------------------------------------------------------------------------------------
@@ -71,36 +104,56 @@ struct SolverArgs {
   int B, C, Cout, HW;
 };
 
+// One element of the solver step (identical op sequence for the scalar and the 4-wide kernel).
+__device__ __forceinline__ void solver_elem(const SolverArgs& a, float e, float eu, float x, float al, float sg, float sa,
+                                            float ss, float& e_out, float& x0, float& xn) {
+  if (a.out_u) e = __fadd_rn(eu, __fmul_rn(a.cfg, __fsub_rn(e, eu)));  // predictor.py:42 / models.py:45
+  // promotion: fp32 model output makes every op fp32; the table entries are exact in fp32
+  if (a.pred_type == 0) x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(sg, e)), al);       // utils.py:51
+  else  // utils.py:55: alphas * sample is a low-precision product when both operands are low precision
+    x0 = __fsub_rn(rn_dt(__fmul_rn(al, x), a.table_dt == a.x_dt ? a.x_dt : TDM_F32), __fmul_rn(sg, e));
+  e_out = e;
+  xn = __fadd_rn(__fmul_rn(sa, x0), __fmul_rn(ss, e));  // scheduler.add_noise, cast by the caller (models.py:58)
+}
+
+template <int VEC>
 __global__ void solver_step_kernel(SolverArgs a) {
   const long per = (long)a.C * a.HW;
-  const long total = (long)a.B * per;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const long total = (long)a.B * per / VEC;
+  for (long iv = (long)blockIdx.x * blockDim.x + threadIdx.x; iv < total; iv += (long)gridDim.x * blockDim.x) {
+    const long i = iv * VEC;
     const int b = int(i / per);
     const long r = i - (long)b * per;  // c*HW + hw; the eps half is the first C channels of Cout
     const long src = (long)b * a.Cout * a.HW + r;
-    float e = a.out_c[src];
-    if (a.out_u) {
-      const float eu = a.out_u[src];
-      e = __fadd_rn(eu, __fmul_rn(a.cfg, __fsub_rn(e, eu)));  // predictor.py:42 / models.py:45
-    }
     const long t = wrap_index(a.t[b], a.table_len);
-    // promotion: fp32 model output makes every op fp32; the table entries are exact in fp32
     const float sg = rd_dt(a.sigmas, t, a.table_dt);
     const float al = rd_dt(a.alphas, t, a.table_dt);
-    const float x = rd_dt(a.x_t, i, a.x_dt);
-    float x0;
-    if (a.pred_type == 0) x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(sg, e)), al);       // utils.py:51
-    else  // utils.py:55: alphas * sample is a low-precision product when both operands are low precision
-      x0 = __fsub_rn(rn_dt(__fmul_rn(al, x), a.table_dt == a.x_dt ? a.x_dt : TDM_F32), __fmul_rn(sg, e));
-    if (a.eps_out) a.eps_out[i] = e;
-    if (a.x0_out) a.x0_out[i] = x0;
+    float sa = 0.f, ss = 0.f;
     if (a.x_next) {
-      const long tn = wrap_index(a.t_next[b], a.table_len);
-      const float ac = a.acp[tn];
-      const float sa = __fsqrt_rn(ac);                  // alphas_cumprod[t] ** 0.5  (torch: pow 0.5 == sqrt)
-      const float ss = __fsqrt_rn(__fsub_rn(1.f, ac));  // (1 - alphas_cumprod[t]) ** 0.5
-      const float xn = __fadd_rn(__fmul_rn(sa, x0), __fmul_rn(ss, e));
-      wr_dt(a.x_next, i, xn, a.next_dt);                // .to(lowp), models.py:58
+      const float ac = a.acp[wrap_index(a.t_next[b], a.table_len)];
+      sa = __fsqrt_rn(ac);                  // alphas_cumprod[t] ** 0.5  (torch: pow 0.5 == sqrt)
+      ss = __fsqrt_rn(__fsub_rn(1.f, ac));  // (1 - alphas_cumprod[t]) ** 0.5
+    }
+    float e[VEC], eu[VEC], x[VEC], eo[VEC], x0[VEC], xn[VEC];
+    if (VEC == 4) {
+      ld4_dt(a.out_c, src, TDM_F32, e);
+      if (a.out_u) ld4_dt(a.out_u, src, TDM_F32, eu);
+      ld4_dt(a.x_t, i, a.x_dt, x);
+    } else {
+      e[0] = a.out_c[src];
+      if (a.out_u) eu[0] = a.out_u[src];
+      x[0] = rd_dt(a.x_t, i, a.x_dt);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) solver_elem(a, e[k], a.out_u ? eu[k] : 0.f, x[k], al, sg, sa, ss, eo[k], x0[k], xn[k]);
+    if (VEC == 4) {
+      if (a.eps_out) st4_dt(a.eps_out, i, TDM_F32, eo);
+      if (a.x0_out) st4_dt(a.x0_out, i, TDM_F32, x0);
+      if (a.x_next) st4_dt(a.x_next, i, a.next_dt, xn);
+    } else {
+      if (a.eps_out) a.eps_out[i] = eo[0];
+      if (a.x0_out) a.x0_out[i] = x0[0];
+      if (a.x_next) wr_dt(a.x_next, i, xn[0], a.next_dt);
     }
   }
 }
@@ -132,9 +185,11 @@ __device__ __forceinline__ int promote(int a, int b) {  // torch type promotion 
   return TDM_F32;  // f16 x bf16 also promotes to f32
 }
 
+template <int VEC>
 __global__ void renoise_kernel(RenoiseArgs a) {
-  const long total = a.B * a.per;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const long total = a.B * a.per / VEC;
+  for (long iv = (long)blockIdx.x * blockDim.x + threadIdx.x; iv < total; iv += (long)gridDim.x * blockDim.x) {
+    const long i = iv * VEC;
     const int b = int(i / a.per);
     const int td = a.table_dt;
     const long t1 = wrap_index(a.t1[b], a.table_len), t2 = wrap_index(a.t2[b], a.table_len);
@@ -150,17 +205,26 @@ __global__ void renoise_kernel(RenoiseArgs a) {
       if (si < 0) si += a.n_states;
     }
     const int sd = a.state_dt[si];
-    const float x = rd_dt(a.states[si], i, sd);
-    const float nz = rd_dt(a.noise, i, a.noise_dt);
     const int d1 = promote(sd, td);
-    // samples / alphas * alphas_new
-    const float y = rn_dt(__fmul_rn(rn_dt(__fdiv_rn(x, a1), d1), a2), d1);
     const int dn = promote(td, a.noise_dt);
-    const float bn = rn_dt(__fmul_rn(beta, nz), dn);
     const int d2 = promote(d1, dn);
-    float r = rn_dt(__fadd_rn(y, bn), d2);
-    if (a.mixed) r = rn_dt(__fdiv_rn(r, s2), promote(d2, td));  // predictor.py:96
-    wr_dt(a.out, i, r, a.out_dt);
+    float x[VEC], nz[VEC], r[VEC];
+    if (VEC == 4) {
+      ld4_dt(a.states[si], i, sd, x);
+      ld4_dt(a.noise, i, a.noise_dt, nz);
+    } else {
+      x[0] = rd_dt(a.states[si], i, sd);
+      nz[0] = rd_dt(a.noise, i, a.noise_dt);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float y = rn_dt(__fmul_rn(rn_dt(__fdiv_rn(x[k], a1), d1), a2), d1);  // samples / alphas * alphas_new
+      const float bn = rn_dt(__fmul_rn(beta, nz[k]), dn);
+      r[k] = rn_dt(__fadd_rn(y, bn), d2);
+      if (a.mixed) r[k] = rn_dt(__fdiv_rn(r[k], s2), promote(d2, td));  // predictor.py:96
+    }
+    if (VEC == 4) st4_dt(a.out, i, a.out_dt, r);
+    else wr_dt(a.out, i, r[0], a.out_dt);
   }
 }
 
@@ -182,6 +246,7 @@ struct LossArgs {
   float* grad;        // optional [B, per]
   float grad_scale;   // upstream scale on the gradient (loss scaling / accumulation)
   long per, B;
+  int vec4;           // per % 4 == 0 and 16-byte aligned inputs: 128-bit loads
 };
 
 __device__ __forceinline__ double block_sum_double(double v) {
@@ -203,6 +268,18 @@ __global__ void loss_weight_kernel(LossArgs a) {  // grid (chunks, B)
   const float* sd = a.sd + (long)b * a.per;
   const float* su = a.sdu + (long)b * a.per;
   double acc = 0.0;
+  if (a.vec4) {  // 128-bit loads; the per-element op sequence is unchanged
+    for (long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < a.per; i += (long)gridDim.x * blockDim.x * 4) {
+      const float4 mv = *reinterpret_cast<const float4*>(m + i), sv = *reinterpret_cast<const float4*>(sd + i),
+                   uv = *reinterpret_cast<const float4*>(su + i);
+      const float mm[4] = {mv.x, mv.y, mv.z, mv.w}, ss[4] = {sv.x, sv.y, sv.z, sv.w}, uu[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float sc = __fadd_rn(ss[k], __fmul_rn(a.cfg_m1, __fsub_rn(ss[k], uu[k])));
+        acc += fabs((double)mm[k] - (double)sc);
+      }
+    }
+  } else
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < a.per; i += (long)gridDim.x * blockDim.x) {
     // sd_latents_cfg = sd + (cfg-1) * (sd - sd_u), fp32 op by op (main.py:518)
     const float sc = __fadd_rn(sd[i], __fmul_rn(a.cfg_m1, __fsub_rn(sd[i], su[i])));
@@ -309,7 +386,11 @@ extern "C" int tdm_solver_step(const float* model_out, const float* model_out_un
   a.eps_out = eps_out; a.x0_out = x0_out; a.x_next = x_next; a.next_dt = next_dtype;
   a.B = B; a.C = C; a.Cout = Cout; a.HW = HW;
   const long total = (long)B * C * HW;
-  ::tdm::count_launch(); solver_step_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  const bool vec = (HW % 4 == 0) && ((((uintptr_t)model_out | (uintptr_t)model_out_uncond | (uintptr_t)x_t | (uintptr_t)eps_out |
+                                       (uintptr_t)x0_out | (uintptr_t)x_next) & 15) == 0);
+  ::tdm::count_launch();
+  if (vec) solver_step_kernel<4><<<ew_grid(total / 4, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  else solver_step_kernel<1><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -331,7 +412,11 @@ extern "C" int tdm_renoise(const void* const* states, const int* state_dtypes, i
   a.n_states = n_states; a.index = index; a.noise = noise; a.noise_dt = noise_dtype; a.t1 = t1; a.t2 = t2;
   a.alphas = alphas; a.sigmas = sigmas; a.table_dt = table_dtype; a.table_len = table_len; a.out = out;
   a.out_dt = out_dtype; a.mixed = mixed; a.per = per_sample; a.B = B;
-  ::tdm::count_launch(); renoise_kernel<<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  bool vec = (per_sample % 4 == 0) && ((((uintptr_t)noise | (uintptr_t)out) & 15) == 0);
+  for (int i = 0; i < n_states; ++i) vec = vec && (((uintptr_t)states[i] & 15) == 0);
+  ::tdm::count_launch();
+  if (vec) renoise_kernel<4><<<ew_grid((long)B * per_sample / 4, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  else renoise_kernel<1><<<ew_grid((long)B * per_sample, 256), 256, 0, (cudaStream_t)stream>>>(a);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -350,6 +435,7 @@ extern "C" int tdm_loss_fwd_bwd(const float* model_latents, const float* sd_late
   a.c = (float)huber_c; a.c2 = (float)(huber_c * huber_c);
   a.wsum = scratch_w; a.loss = loss_out; a.grad = grad_out; a.grad_scale = grad_scale;
   a.per = per_sample; a.B = B;
+  a.vec4 = (per_sample % 4 == 0) && ((((uintptr_t)model_latents | (uintptr_t)sd_latents | (uintptr_t)sd_latents_uncond) & 15) == 0);
   int chunks = (int)((per_sample + 2047) / 2048);
   if (chunks > 64) chunks = 64;
   dim3 grid(chunks, B);
