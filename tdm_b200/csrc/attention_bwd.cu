@@ -30,8 +30,11 @@ struct AttnBwdParams {
 };
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; the same thread also zero-fills its d-wide slice of the fp32 dQ
+// accumulator (layout [B*Sq, H*d]), which saves a separate memset node between the kernels.
 __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, long sb, long ss, long sh,
-                                  float* __restrict__ delta, int B, int H, int Sq, int d) {
+                                  float* __restrict__ delta, float* __restrict__ dq_accum, int B, int H, int Sq, int d) {
+  pdl_sync();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
   const long total = (long)B * Sq * H;
   if (idx >= total) return;
@@ -48,6 +51,8 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
     acc += o0.x * g0.x + o0.y * g0.y + o1.x * g1.x + o1.y * g1.y + o2.x * g2.x + o2.y * g2.y + o3.x * g3.x + o3.y * g3.y;
   }
   delta[((long)b * H + h) * Sq + q] = acc;
+  float4* z = reinterpret_cast<float4*>(dq_accum + (((long)b * Sq + q) * H + h) * d);  // d % 8 == 0: 16-byte aligned
+  for (int c = 0; c < d / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __global__ void __launch_bounds__(192, 1)
@@ -316,6 +321,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 336,
                  tm_dQ = tmem_base + 416;
+  pdl_sync();
 
   if (warp == 12) {
     // ===================== TMA producer =====================
@@ -540,6 +546,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 // fp32 [rows, cols] (ld_in) -> bf16 [rows, cols] (ld_out): dQ scratch -> its slot in the d(qkv) matrix
 __global__ void cast2d_f32_bf16_kernel(const float* in, long ld_in, bf16* out, long ld_out, int rows, int cols) {
+  pdl_sync();
   const int c4 = cols / 4;
   const long total = (long)rows * c4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -573,11 +580,11 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   const int HD = a->H * a->d;
   {
     const long total = rows * a->H;
-    ::tdm::count_launch(); attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const bf16*)a->O, (const bf16*)a->dO, a->o_stride_b,
-                                                                     a->o_stride_s, a->o_stride_h, a->delta, a->B, a->H,
-                                                                     a->Sq, a->d);
+    ::tdm::count_launch();
+    TDM_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, s, (const bf16*)a->O,
+                              (const bf16*)a->dO, (long)a->o_stride_b, (long)a->o_stride_s, (long)a->o_stride_h, a->delta,
+                              a->dq_accum, a->B, a->H, a->Sq, a->d));
   }
-  TDM_CHECK_CUDA(cudaMemsetAsync(a->dq_accum, 0, sizeof(float) * rows * HD, s));
   AttnBwdParams p;
   p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d;
   p.nd = (a->d + 63) / 64; p.dk16 = (a->d + 15) / 16;
@@ -593,7 +600,8 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
       TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       smem_set = smem;
     }
-    ::tdm::count_launch(); attn_bwd_kernel<<<grid, BWD_THREADS, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
+    ::tdm::count_launch();
+    TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, p));
   } else {
     const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
     static int smem_set_w = 0;
@@ -606,7 +614,8 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   TDM_CHECK_CUDA(cudaGetLastError());
   // dQ scratch [B*Sq, H*d] fp32 -> bf16 dQ with the caller's strides (requires the [tokens, H*d] layout)
   const int nblk = num_sms() * 8;
-  ::tdm::count_launch(); cast2d_f32_bf16_kernel<<<nblk, 256, 0, s>>>(a->dq_accum, HD, (bf16*)a->dQ, a->dq_stride_s, (int)rows, HD);
+  ::tdm::count_launch();
+  TDM_CHECK_CUDA(launch_pdl(cast2d_f32_bf16_kernel, dim3(nblk), dim3(256), (size_t)0, s, (const float*)a->dq_accum, (long)HD, (bf16*)a->dQ, (long)a->dq_stride_s, (int)rows, (int)HD));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -105,6 +105,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base;        // 2 x 128 columns
   const uint32_t tmem_O = tmem_base + 256;  // <= 128 columns
+  pdl_sync();
 
   if (warp == 8) {
     // ===================== TMA producer =====================
@@ -391,7 +392,8 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   }
   const long items = (long)((a->Sq + ATT_BM - 1) / ATT_BM) * a->H * a->B;
   const int grid = (int)(items < num_sms() ? items : num_sms());
-  ::tdm::count_launch(); attn_fwd_kernel<<<grid, FWD_THREADS, smem, (cudaStream_t)stream>>>(tmQ, tmK, tmV, p);
+  ::tdm::count_launch();
+  TDM_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -2,6 +2,7 @@
 // point (no link-time dependency on libcuda).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -23,6 +24,15 @@ unsigned long long launches(int reset) {
   unsigned long long v = __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
   if (reset) __atomic_store_n(&g_launches, 0ull, __ATOMIC_RELAXED);
   return v;
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TDM_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int num_sms() {

@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __res
                                                             int rows_per_sample, bf16* __restrict__ out,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             int M, int D, float eps) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) ln_modulate_bwd_kernel(const bf16* __rest
                                                             const float* __restrict__ scale, long mod_stride, int rows_per_sample,
                                                             const float* __restrict__ dx_in, float* __restrict__ dx_out,
                                                             bf16* __restrict__ dx_out_bf16, int M, int D) {
+  pdl_sync();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -143,6 +145,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) colreduce_kernel(ColRedArgs a) {
   __shared__ float4 sm0[8][32];
   __shared__ float4 sm1[8][32];
+  pdl_sync();
   const int col = blockIdx.x * 128 + threadIdx.x * 4;
   const int row0 = blockIdx.y * a.rows_per_block;
   const int b = row0 / a.rows_per_sample;
@@ -214,7 +217,8 @@ template <int MODE>
 static int launch_colreduce(ColRedArgs a, cudaStream_t s) {
   a.rows_per_block = pick_rows_per_block(a.rows_per_sample);
   dim3 grid((a.D + 127) / 128, (a.M + a.rows_per_block - 1) / a.rows_per_block);
-  ::tdm::count_launch(); colreduce_kernel<MODE><<<grid, dim3(32, 8), 0, s>>>(a);
+  ::tdm::count_launch();
+  TDM_CHECK_CUDA(launch_pdl(colreduce_kernel<MODE>, grid, dim3(32, 8), (size_t)0, s, a));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -224,6 +228,7 @@ static int launch_colreduce(ColRedArgs a, cudaStream_t s) {
 // ---------------------------------------------------------------------------------------------
 // mod[b, j, d] = table[j, d] + (per_j ? tvec[b, j*D + d] : tvec[b, d])
 __global__ void modulation_kernel(const float* table, const float* tvec, int per_j, float* out, int B, int J, int D) {
+  pdl_sync();
   const long total = (long)B * J * D;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int d = int(i % D);
@@ -235,6 +240,7 @@ __global__ void modulation_kernel(const float* table, const float* tvec, int per
 // dtable[j,d] += sum_b dmod[b,j,d];  dtvec (+)= dmod (per_j) or sum_j dmod (broadcast)
 __global__ void modulation_bwd_kernel(const float* dmod, float* dtable, float* dtvec, int per_j, int accumulate_tvec,
                                       int B, int J, int D) {
+  pdl_sync();
   const long jd = (long)J * D;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < jd; i += (long)gridDim.x * blockDim.x) {
     float s = 0.f;
@@ -346,8 +352,8 @@ extern "C" int tdm_ln_modulate_fwd(const float* x, const float* shift, const flo
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_fwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE(M > 0 && rows_per_sample > 0 && mod_stride % 4 == 0, "tdm_ln_modulate_fwd: bad shape");
   ::tdm::count_launch();
-#define TDM_LN_FWD(NVV) ln_modulate_fwd_kernel<NVV><<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>( \
-      x, shift, scale, mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, D, eps)
+#define TDM_LN_FWD(NVV) TDM_CHECK_CUDA(launch_pdl(ln_modulate_fwd_kernel<NVV>, dim3((M + 7) / 8), dim3(256), (size_t)0, (cudaStream_t)stream, \
+      x, shift, scale, (long)mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, D, eps))
   switch (D >> 7) {
     case 2: TDM_LN_FWD(2); break;
     case 9: TDM_LN_FWD(9); break;
@@ -367,8 +373,8 @@ extern "C" int tdm_ln_modulate_bwd(const void* dh_bf16, const float* x, const fl
   TDM_REQUIRE((dshift == nullptr) == (dscale == nullptr), "tdm_ln_modulate_bwd: dshift and dscale come together");
   cudaStream_t s = (cudaStream_t)stream;
   ::tdm::count_launch();
-#define TDM_LN_BWD(NVV) ln_modulate_bwd_kernel<NVV><<<(M + 7) / 8, 256, 0, s>>>( \
-      (const bf16*)dh_bf16, x, mean, rstd, scale, mod_stride, rows_per_sample, dx_in, dx_out, (bf16*)dx_out_bf16, M, D)
+#define TDM_LN_BWD(NVV) TDM_CHECK_CUDA(launch_pdl(ln_modulate_bwd_kernel<NVV>, dim3((M + 7) / 8), dim3(256), (size_t)0, s, \
+      (const bf16*)dh_bf16, x, mean, rstd, scale, (long)mod_stride, rows_per_sample, dx_in, dx_out, (bf16*)dx_out_bf16, M, D))
   switch (D >> 7) {
     case 2: TDM_LN_BWD(2); break;
     case 9: TDM_LN_BWD(9); break;
@@ -409,7 +415,8 @@ extern "C" int tdm_colsum_bf16(const void* a_bf16, int64_t ld, int M, int N, flo
 extern "C" int tdm_modulation(const float* table, const float* tvec, int per_j, float* out, int B, int J, int D,
                               void* stream) {
   TDM_REQUIRE(table && tvec && out, "tdm_modulation: null input");
-  ::tdm::count_launch(); modulation_kernel<<<ew_grid((long)B * J * D, 256), 256, 0, (cudaStream_t)stream>>>(table, tvec, per_j, out, B, J, D);
+  ::tdm::count_launch();
+  TDM_CHECK_CUDA(launch_pdl(modulation_kernel, dim3(ew_grid((long)B * J * D, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, table, tvec, per_j, out, B, J, D));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }
@@ -417,8 +424,9 @@ extern "C" int tdm_modulation(const float* table, const float* tvec, int per_j, 
 extern "C" int tdm_modulation_bwd(const float* dmod, float* dtable, float* dtvec, int per_j, int accumulate_tvec,
                                   int B, int J, int D, void* stream) {
   TDM_REQUIRE(dmod, "tdm_modulation_bwd: null input");
-  ::tdm::count_launch(); modulation_bwd_kernel<<<ew_grid((long)J * D, 256), 256, 0, (cudaStream_t)stream>>>(dmod, dtable, dtvec, per_j,
-                                                                                   accumulate_tvec, B, J, D);
+  ::tdm::count_launch();
+  TDM_CHECK_CUDA(launch_pdl(modulation_bwd_kernel, dim3(ew_grid((long)J * D, 256)), dim3(256), (size_t)0, (cudaStream_t)stream, dmod, dtable,
+                            dtvec, per_j, accumulate_tvec, B, J, D));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

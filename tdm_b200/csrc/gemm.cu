@@ -270,6 +270,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();  // everything above is private to this CTA; global memory is touched only from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -479,6 +480,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   cluster_sync_all();  // both CTAs' barriers and tensor memory exist before anyone signals or writes across the pair
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -700,14 +702,16 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
       attr_set = true;
     }
     const int pairs = units < sms / 2 ? units : sms / 2;
-    ::tdm::count_launch(); gemm2_bf16_kernel<BN><<<2 * pairs, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC16, tmC32, p);
+    ::tdm::count_launch();
+    TDM_CHECK_CUDA(launch_pdl(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(GEMM_THREADS), SMEM, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, p));
   } else {
     if (!attr_set) {
       TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
       attr_set = true;
     }
     const int grid = units < sms ? units : sms;
-    ::tdm::count_launch(); gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, SMEM, stream>>>(tmA, tmB, tmA2, tmB2, tmC16, tmC32, p);
+    ::tdm::count_launch();
+    TDM_CHECK_CUDA(launch_pdl(gemm_bf16_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SMEM, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, p));
   }
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
