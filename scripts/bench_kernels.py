@@ -4,23 +4,18 @@ import json
 import sys
 import torch
 sys.path.insert(0, ".")
+sys.path.insert(0, "scripts")
 from tdm_b200 import ops
 
 DEV = "cuda"
 NB = 4
 
 
+from _timing import timeit as _timeit
+
+
 def timeit(fn, iters=20, warm=3):
-    for i in range(warm):
-        fn(i)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        fn(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1e3  # us
+    return _timeit(fn, iters, warm)[0]
 
 
 def gemm_case(name, M, N, K, epi, tile_n=0, cta_pair=0):

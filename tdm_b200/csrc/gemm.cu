@@ -8,6 +8,7 @@
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill plus predicated stores.
 #include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tdm {
@@ -22,6 +23,13 @@ struct GemmParams {
   int seg_n, seg_k2;
   int num_m_tiles, num_n_tiles;
   int splits;        // split-K factor (>1 only in accumulate-only mode: partial sums are red.add'ed into out_f32)
+  int stages;        // depth of the TMA<->MMA shared-memory ring (chosen on the host: what the epilogue leaves free)
+  int epi_bytes;     // bytes of epilogue staging that follow the ring
+  // streaming epilogue (FAST kernels): per warp a ring of `epi_nbuf` chunk sets of `epi_set_bytes`; a set holds the
+  // fp32 tile (residual in -> out_f32, at 0), the first bf16 tile (act_in in -> out_bf16, at epi_off_h0) and the
+  // second bf16 tile (pre_out, at epi_off_h1); `epi_in_bytes` = bytes the TMA loads per chunk (0: nothing to load)
+  int epi_nbuf, epi_set_bytes, epi_off_h0, epi_off_h1, epi_in_bytes;
+  int epi_feat_slot;  // which specialised instance of the streaming epilogue runs (-1: the run-time tested one)
   int gate_uniform;  // rows_per_gate % BM == 0: one gate row per tile
   float alpha;
   int act;
@@ -55,19 +63,24 @@ constexpr int EPI_STAGE_F32 = 32 * 32 * 4;                        // 4 KB
 constexpr int EPI_STAGE_BF16 = 32 * 32 * 2;                       // 2 KB
 constexpr int EPI_STAGE_WARP = EPI_STAGE_F32 + EPI_STAGE_BF16;    // 6 KB per warp
 constexpr int EPI_VEC_FLOATS = 256;                               // >= widest tile
-constexpr int EPI_SMEM_BYTES = EPI_WARPS * EPI_STAGE_WARP + 2 * 2 * EPI_VEC_FLOATS * 4;  // 48 KB + 4 KB
+constexpr int EPI_GENERIC_BYTES = EPI_WARPS * EPI_STAGE_WARP;   // 48 KB: staging of the generic epilogue
+constexpr int EPI_VEC_BYTES = 8192;  // generic: double-buffered bias / gate rows (4 KB); FAST: 1 KB of private rows per warp
+constexpr int MAX_STAGES = 8;
+constexpr int EPI_MAX_NBUF = 3;
+constexpr int BAR_BYTES = 512;  // full[8] empty[8] tfull[2] tempty[2] ld[8 warps x 3] tmem slot
+constexpr int SMEM_LIMIT = 232448;  // 227 KB dynamic shared memory per CTA on sm_100
+// shared memory: [ring: stages x STAGE_BYTES][epilogue staging: epi_bytes][bias/gate rows][barriers]
+__host__ __device__ constexpr int gemm_smem_bytes(int stages, int stage_bytes, int epi_bytes) {
+  return stages * stage_bytes + epi_bytes + EPI_VEC_BYTES + BAR_BYTES + 1024 /*align*/;
+}
 
 template <int BN>
 struct GemmCfg {
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 3 : (BN >= 192 ? 4 : (BN >= 128 ? 5 : 7));  // 52 KB go to the epilogue
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128 ? 128 : 256);  // TMEM columns between the two accumulators
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int STAGING_BYTES = EPI_SMEM_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
 };
 
 __device__ __forceinline__ float gelu_tanh_fast(float x) {
@@ -139,13 +152,7 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CU
       const bool ok = row_ok && n < p.N;  // guards every direct global access; staged stores are clipped by the TMA
       float v[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = p.alpha * __uint_as_float(acc[g * 8 + i]);
-      {
-        const float4 b0 = *reinterpret_cast<const float4*>(sb + c + g * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(sb + c + g * 8 + 4);
-        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-      }
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(p.alpha, __uint_as_float(acc[g * 8 + i]), sb[c + g * 8 + i]);  // as the streaming epilogue
       if (p.pre_out && ok) {
         uint4 o;
         o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]);
@@ -191,14 +198,14 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CU
           g0 = *reinterpret_cast<const float4*>(sg + c + g * 8);
           g1 = *reinterpret_cast<const float4*>(sg + c + g * 8 + 4);
         }
-        v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-        v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+        v[0] = __fmul_rn(v[0], g0.x); v[1] = __fmul_rn(v[1], g0.y); v[2] = __fmul_rn(v[2], g0.z); v[3] = __fmul_rn(v[3], g0.w);
+        v[4] = __fmul_rn(v[4], g1.x); v[5] = __fmul_rn(v[5], g1.y); v[6] = __fmul_rn(v[6], g1.z); v[7] = __fmul_rn(v[7], g1.w);
       }
       if (p.res && ok) {
         const float4 r0 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n);
         const float4 r1 = *reinterpret_cast<const float4*>(p.res + rr * p.ld_res + n + 4);
-        v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-        v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        v[0] = __fadd_rn(v[0], r0.x); v[1] = __fadd_rn(v[1], r0.y); v[2] = __fadd_rn(v[2], r0.z); v[3] = __fadd_rn(v[3], r0.w);
+        v[4] = __fadd_rn(v[4], r1.x); v[5] = __fadd_rn(v[5], r1.y); v[6] = __fadd_rn(v[6], r1.z); v[7] = __fadd_rn(v[7], r1.w);
       }
       if (p.out_f32) {
         *reinterpret_cast<float4*>(stg_f + (((2 * g) ^ xf) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -221,23 +228,346 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CU
   }
 }
 
-template <int BN>
+// ------------------------------------------------------------------------------------------------
+// Streaming epilogue (FAST kernels).  Everything that touches global memory is a TMA transfer of a 32 x 32 chunk:
+// the residual and the backward-activation input are LOADED into the chunk set one chunk ahead (the first chunk of a
+// tile before the accumulator is even waited for), every output is written into the set in place and drained by a
+// TMA store; sets form a ring of 2-3 per warp so a store is never waited for right after it was issued.  The next
+// chunk's tcgen05.ld is in flight while the current one is processed, and the accumulator is handed back to the MMA
+// warp as soon as this warp's last chunk sits in registers.  All option tests are warp-uniform and made once per
+// chunk, shared memory is addressed through 32-bit shared-space instructions: ~110 SASS instructions per chunk for a
+// bias + bf16 epilogue (the generic epilogue below: ~620, and it was the bottleneck of every K <= 1152 GEMM).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_wait_read_n(int n) {  // at most n of this thread's store groups still reading
+  if (n <= 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  else if (n == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+  else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+}
+
+#ifdef TDM_DBG_TIMING
+__device__ long long tdm_dbg_times[8192];
+__device__ uint32_t tdm_dbg_cj[32 * 8];
+#define DBG_T(tag)                                                                  \
+  do {                                                                              \
+    if (blockIdx.x == 3 && lane == 0 && q == 1 && ch == 0 && cj < 500)              \
+      tdm_dbg_times[cj * 8 + (tag)] = clock64();                                    \
+  } while (0)
+#else
+#define DBG_T(tag)
+#endif
+
+struct EpiMaps {
+  const CUtensorMap *c16, *c32, *res, *act, *pre;
+};
+
+// Feature sets the streaming epilogue is compiled for.  The hot GEMMs of a DiT block hit one of the exact sets and run
+// branch-free chunk code; any other combination takes FEAT_DYN, the same code with the tests made at run time.
+enum : int {
+  EF_OUT16 = 1, EF_OUT32 = 2, EF_RES = 4, EF_GATE = 8, EF_PRE = 16, EF_GELU = 32, EF_GELU_BWD = 64, FEAT_DYN = 1 << 20
+};
+__host__ __device__ constexpr int epi_feat_slot(int feat) {  // index of the specialised instance, -1: dynamic
+  switch (feat) {
+    case EF_OUT16: return 0;                                  // QKV, q2, kv2, plain dgrads, LoRA t / dt
+    case EF_OUT16 | EF_GELU: return 1;                        // FF1
+    case EF_OUT16 | EF_GELU | EF_PRE: return 2;               // FF1, pre-activation kept for the backward
+    case EF_OUT16 | EF_GELU_BWD: return 3;                    // FF2 dgrad
+    case EF_OUT32 | EF_RES: return 4;                         // o2, q2 dgrad, un-split wgrad accumulation
+    case EF_OUT32 | EF_RES | EF_GATE: return 5;               // FF2
+    case EF_OUT32 | EF_RES | EF_GATE | EF_OUT16: return 6;    // O-proj
+    case EF_OUT16 | EF_RES: return 7;                         // LoRA merge: bf16(W32 + s B A)
+    default: return -1;
+  }
+}
+
+// One tile, one epilogue warp.  `ring` / `ldbar` are this warp's chunk sets and load barriers, `cj` its running
+// chunk count (ring position and barrier phase), `vec` its private bias / gate rows (chunk k of the tile at
+// vec + k * 256: 32 bias floats, 32 gate floats).  Returns after the last store of the tile has been ISSUED.
+template <int BN, bool PAIR, int FEAT>
+__device__ __forceinline__ void gemm_epilogue_fast(const GemmParams& p, const EpiMaps& tm, uint32_t taddr, int m0, int n0, int q,
+                                                   int ch, int lane, uint32_t ring, uint64_t* ldbar, uint32_t& buf, uint32_t& ph,
+                                                   uint32_t vec, uint64_t* tfull, uint32_t aphase, uint64_t* tempty) {
+  constexpr bool DYN = FEAT == FEAT_DYN;
+  const bool f_out16 = DYN ? p.out_bf16 != nullptr : bool(FEAT & EF_OUT16);
+  const bool f_out32 = DYN ? p.out_f32 != nullptr : bool(FEAT & EF_OUT32);
+  const bool f_res = DYN ? p.res != nullptr : bool(FEAT & EF_RES);
+  const bool f_gate = DYN ? p.gate != nullptr : bool(FEAT & EF_GATE);
+  const bool f_pre = DYN ? p.pre_out != nullptr : bool(FEAT & EF_PRE);
+  const bool f_gelu = DYN ? p.act == TDM_ACT_GELU_TANH : bool(FEAT & EF_GELU);
+  const bool f_gelu_bwd = DYN ? p.act == TDM_ACT_GELU_TANH_BWD : bool(FEAT & EF_GELU_BWD);
+  const bool f_silu = DYN ? p.act == TDM_ACT_SILU : false;
+  const bool f_silu_bwd = DYN ? p.act == TDM_ACT_SILU_BWD : false;
+  const bool f_actin = f_gelu_bwd || f_silu_bwd;
+  const bool has_in = f_res || f_actin;
+  const int row0 = m0 + q * 32;
+  const int nlim = (p.N - n0) < BN ? (p.N - n0) : BN;  // columns of this tile that exist
+  const uint32_t nbuf = (uint32_t)p.epi_nbuf;
+#ifdef TDM_DBG_TIMING
+  uint32_t& cj = tdm_dbg_cj[(blockIdx.x % 32) * EPI_WARPS + q + 4 * ch];
+#endif
+  const uint32_t xf = (lane & 7) << 4, xh = ((lane >> 1) & 3) << 4;  // SW128 / SW64 XOR of this thread's row
+  int c = ch * 32;
+  auto hand_back = [&]() {  // the accumulator is in registers (or not needed): the MMA warp may overwrite it
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (PAIR) mbar_arrive_cluster(smem_u32(tempty) & PEER_BIT_MASK);  // the leader's barrier
+      else mbar_arrive(tempty);
+    }
+  };
+  auto issue_loads = [&](uint32_t buf, int col) {  // lane 0: residual / activation-input chunk -> set `buf`
+    const uint32_t set = ring + buf * p.epi_set_bytes;
+    uint64_t* bar = &ldbar[buf];
+    mbar_arrive_expect_tx(bar, (uint32_t)p.epi_in_bytes);
+    const uint32_t bar32 = smem_u32(bar);
+    if (f_res)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   ::"r"(set), "l"(reinterpret_cast<uint64_t>(tm.res)), "r"(bar32), "r"(n0 + col), "r"(row0) : "memory");
+    if (f_actin)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   ::"r"(set + p.epi_off_h0), "l"(reinterpret_cast<uint64_t>(tm.act)), "r"(bar32), "r"(n0 + col), "r"(row0) : "memory");
+  };
+  if (c >= nlim) {  // this warp has no chunk in a narrow tail tile
+    mbar_wait_relaxed(tfull, aphase);
+    hand_back();
+    return;
+  }
+  DBG_T(1);
+  if (has_in && lane == 0) {  // the first chunk's inputs travel while the mainloop finishes the accumulator
+    tma_store_wait_read_n(nbuf - 1);
+    issue_loads(buf, c);
+  }
+  mbar_wait_relaxed(tfull, aphase);
+  tc_fence_after();
+  DBG_T(2);
+  uint32_t acc[32];
+  tmem_ld32(taddr + c, acc);
+  uint32_t sb = vec;  // bias row of this chunk (zeros without a bias), the gate row follows (ones without a gate)
+#pragma unroll 1
+  for (; c < nlim; c += 64, sb += 256) {
+    const uint32_t set = ring + buf * p.epi_set_bytes;
+    const uint32_t buf_next = buf + 1 == nbuf ? 0 : buf + 1;
+    const uint32_t rowF = set + lane * 128, rowH0 = set + p.epi_off_h0 + lane * 64, rowH1 = set + p.epi_off_h1 + lane * 64;
+    tmem_ld_wait();
+    DBG_T(3);
+    float v[32];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint4 b = lds128(sb + g * 16);
+      v[g * 4 + 0] = fmaf(p.alpha, __uint_as_float(acc[g * 4 + 0]), __uint_as_float(b.x));
+      v[g * 4 + 1] = fmaf(p.alpha, __uint_as_float(acc[g * 4 + 1]), __uint_as_float(b.y));
+      v[g * 4 + 2] = fmaf(p.alpha, __uint_as_float(acc[g * 4 + 2]), __uint_as_float(b.z));
+      v[g * 4 + 3] = fmaf(p.alpha, __uint_as_float(acc[g * 4 + 3]), __uint_as_float(b.w));
+    }
+    const int cn = c + 64;
+    const bool more = cn < nlim;  // warp-uniform
+    if (more) tmem_ld32(taddr + cn, acc);  // in flight while this chunk is processed
+    else hand_back();
+    if (lane == 0) {
+      if (has_in) {
+        if (more) {
+          tma_store_wait_read_n(nbuf - 2);  // the set of chunk cj + 1 was last stored from by chunk cj + 1 - nbuf
+          issue_loads(buf_next, cn);
+        }
+      } else {
+        tma_store_wait_read_n(nbuf - 1);  // this set was last stored from by chunk cj - nbuf
+      }
+    }
+    __syncwarp();
+    DBG_T(4);
+    if (has_in) mbar_wait(&ldbar[buf], ph);
+    if (f_pre) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(rowH1 + ((j << 4) ^ xh), pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+               pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+    }
+    if (f_gelu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = gelu_tanh_fast(v[i]);
+    } else if (f_actin) {
+      float u[32];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 w = lds128(rowH0 + ((j << 4) ^ xh));
+        const float2 u0 = unpack_bf16(w.x), u1 = unpack_bf16(w.y), u2 = unpack_bf16(w.z), u3 = unpack_bf16(w.w);
+        u[j * 8 + 0] = u0.x; u[j * 8 + 1] = u0.y; u[j * 8 + 2] = u1.x; u[j * 8 + 3] = u1.y;
+        u[j * 8 + 4] = u2.x; u[j * 8 + 5] = u2.y; u[j * 8 + 6] = u3.x; u[j * 8 + 7] = u3.y;
+      }
+      if (f_gelu_bwd) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] *= gelu_tanh_grad_fast(u[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sgm = 1.f / (1.f + __expf(-u[i]));
+          v[i] *= sgm * (1.f + u[i] * (1.f - sgm));
+        }
+      }
+    } else if (f_silu) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = v[i] / (1.f + __expf(-v[i]));
+    }
+    if (f_gate) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 w = lds128(sb + 128 + g * 16);
+        v[g * 4 + 0] = __fmul_rn(v[g * 4 + 0], __uint_as_float(w.x)); v[g * 4 + 1] = __fmul_rn(v[g * 4 + 1], __uint_as_float(w.y));
+        v[g * 4 + 2] = __fmul_rn(v[g * 4 + 2], __uint_as_float(w.z)); v[g * 4 + 3] = __fmul_rn(v[g * 4 + 3], __uint_as_float(w.w));
+      }
+    }
+    if (f_res) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 w = lds128(rowF + ((g << 4) ^ xf));
+        v[g * 4 + 0] = __fadd_rn(v[g * 4 + 0], __uint_as_float(w.x)); v[g * 4 + 1] = __fadd_rn(v[g * 4 + 1], __uint_as_float(w.y));
+        v[g * 4 + 2] = __fadd_rn(v[g * 4 + 2], __uint_as_float(w.z)); v[g * 4 + 3] = __fadd_rn(v[g * 4 + 3], __uint_as_float(w.w));
+      }
+    }
+    if (f_out32) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        sts128(rowF + ((g << 4) ^ xf), __float_as_uint(v[g * 4 + 0]), __float_as_uint(v[g * 4 + 1]), __float_as_uint(v[g * 4 + 2]),
+               __float_as_uint(v[g * 4 + 3]));
+    }
+    if (f_out16) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        sts128(rowH0 + ((j << 4) ^ xh), pack_bf16(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16(v[j * 8 + 2], v[j * 8 + 3]),
+               pack_bf16(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16(v[j * 8 + 6], v[j * 8 + 7]));
+    }
+    DBG_T(5);
+    fence_async_smem();
+    __syncwarp();
+    DBG_T(6);
+#ifndef TDM_DBG_NOSTORE
+    if (lane == 0) {
+      const int col = n0 + c;
+      if (f_out32)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tm.c32)), "r"(set), "r"(col), "r"(row0) : "memory");
+      if (f_out16)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tm.c16)), "r"(set + p.epi_off_h0), "r"(col), "r"(row0) : "memory");
+      if (f_pre)
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(tm.pre)), "r"(set + p.epi_off_h1), "r"(col), "r"(row0) : "memory");
+      tma_store_commit();
+    }
+#endif
+    DBG_T(7);
+    buf = buf_next;
+    if (buf == 0) ph ^= 1;
+#ifdef TDM_DBG_TIMING
+    ++cj;
+#endif
+  }
+}
+
+// The epilogue warps' tile loop of a FAST kernel (shared by the single-CTA and the CTA-pair kernel).  Bias / gate
+// rows are private to each warp: the values of the NEXT tile are fetched into registers while the current tile is
+// processed and parked in the warp's own shared-memory rows at the start of that tile -- no CTA-wide barrier.
+template <int BN, bool PAIR>
+__device__ __forceinline__ void gemm_epilogue_warp_loop(const GemmParams& p, const EpiMaps& maps, uint32_t tmem_base, int acc_stride,
+                                                        int ew, int lane, uint32_t ring, uint64_t* ldbar, uint32_t vec,
+                                                        uint64_t* tfull_bar, uint64_t* tempty_bar, int unit0, int unit_step,
+                                                        int num_units, int rank) {
+  constexpr int NCH = (BN + 63) / 64;  // chunks per warp and tile
+  const int q = ew & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+  const int ch = ew >> 2;  // even / odd 32-column chunks of the tile
+  const int feat_slot = p.epi_feat_slot;
+  float bias_r[NCH], gate_r[NCH];
+  // tile coordinates advance incrementally (FAST kernels never split K: unit == tile): no division in the tile loop
+  const int nn = p.num_n_tiles;
+  const int step_m = unit_step / nn, step_n = unit_step - step_m * nn;
+  int mt = unit0 / nn, nt = unit0 - mt * nn;
+  auto fetch_vec = [&](int mt_, int nt_) {
+    const int m0_ = mt_ * (PAIR ? 2 * BM : BM) + rank * BM, n0_ = nt_ * BN;
+    const float* gate_tile = nullptr;
+    if (p.gate) gate_tile = p.gate + (long)(m0_ / p.rows_per_gate) * p.gate_stride;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const int n = n0_ + ch * 32 + k * 64 + lane;
+      const bool ok = n < p.N && ch * 32 + k * 64 < BN;
+      bias_r[k] = (p.bias && ok) ? __ldg(p.bias + n) : 0.f;
+      gate_r[k] = (gate_tile && ok) ? __ldg(gate_tile + n) : 1.f;
+    }
+  };
+  uint32_t buf = 0, ph = 0;
+  int it = 0;
+  if (unit0 < num_units) fetch_vec(mt, nt);
+  for (int unit = unit0; unit < num_units; unit += unit_step, ++it) {
+    const int as = it & 1;
+    const uint32_t aphase = (it >> 1) & 1;
+    const int m0 = mt * (PAIR ? 2 * BM : BM) + rank * BM, n0 = nt * BN;
+    __syncwarp();  // the previous tile's reads of the rows are done
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + k * 256 + lane * 4), "f"(bias_r[k]) : "memory");
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + k * 256 + 128 + lane * 4), "f"(gate_r[k]) : "memory");
+    }
+    __syncwarp();
+    mt += step_m;
+    nt += step_n;
+    if (nt >= nn) {
+      nt -= nn;
+      ++mt;
+    }
+    if (unit + unit_step < num_units) fetch_vec(mt, nt);  // the next tile's rows travel during this tile
+    const uint32_t taddr = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
+#ifndef TDM_DBG_NOEPI
+#define TDM_EPI_CASE(F) \
+  gemm_epilogue_fast<BN, PAIR, F>(p, maps, taddr, m0, n0, q, ch, lane, ring, ldbar, buf, ph, vec, &tfull_bar[as], aphase, &tempty_bar[as])
+    switch (feat_slot) {
+      case 0: TDM_EPI_CASE(EF_OUT16); break;
+      case 1: TDM_EPI_CASE(EF_OUT16 | EF_GELU); break;
+      case 2: TDM_EPI_CASE(EF_OUT16 | EF_GELU | EF_PRE); break;
+      case 3: TDM_EPI_CASE(EF_OUT16 | EF_GELU_BWD); break;
+      case 4: TDM_EPI_CASE(EF_OUT32 | EF_RES); break;
+      case 5: TDM_EPI_CASE(EF_OUT32 | EF_RES | EF_GATE); break;
+      case 6: TDM_EPI_CASE(EF_OUT32 | EF_RES | EF_GATE | EF_OUT16); break;
+      case 7: TDM_EPI_CASE(EF_OUT16 | EF_RES); break;
+      default: TDM_EPI_CASE(FEAT_DYN); break;
+    }
+#undef TDM_EPI_CASE
+#else
+    mbar_wait(&tfull_bar[as], aphase);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (PAIR) mbar_arrive_cluster(smem_u32(&tempty_bar[as]) & PEER_BIT_MASK);
+      else mbar_arrive(&tempty_bar[as]);
+    }
+#endif
+  }
+}
+
+template <int BN, bool FAST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAct,
+                 const __grid_constant__ CUtensorMap tmPre, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned: stages are multiples of 8 KB
-  float* epi_vec = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_STAGE_WARP);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::STAGING_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  float* epi_vec = reinterpret_cast<float*>(epi_stage + p.epi_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + p.epi_bytes + EPI_VEC_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ld_bar = tempty_bar + 2;  // [EPI_WARPS][EPI_MAX_NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + EPI_WARPS * EPI_MAX_NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -254,6 +584,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tma_prefetch_desc(&tmB2);
     }
   }
+  if (FAST && warp == 4 && lane == 0) {
+    if (p.out_bf16) tma_prefetch_desc(&tmC16);
+    if (p.out_f32) tma_prefetch_desc(&tmC32);
+    if (p.res) tma_prefetch_desc(&tmRes);
+    if (p.act_in) tma_prefetch_desc(&tmAct);
+    if (p.pre_out) tma_prefetch_desc(&tmPre);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -263,6 +600,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], EPI_WARPS);
     }
+    if constexpr (FAST)
+      for (int s = 0; s < EPI_WARPS * EPI_MAX_NBUF; ++s) mbar_init(&ld_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
@@ -375,25 +714,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // thread == accumulator row (tcgen05.ld 32x32b): all 32 values of a chunk sit in registers, so the fused math
     // has 32-way ILP and every global access is a 16-byte vector; each thread touches whole 32-byte sectors.
     const int ew = warp - 4;
-    const int q = ew & 3;    // == warp % 4: the TMEM lane quarter this warp may read
-    const int ch = ew >> 2;  // even / odd 32-column chunks of the tile
-    int it = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
-      const int tile = unit / p.splits;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / p.num_n_tiles) * BM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
+    if constexpr (FAST) {
+      const EpiMaps maps = {&tmC16, &tmC32, &tmRes, &tmAct, &tmPre};
+      gemm_epilogue_warp_loop<BN, false>(p, maps, tmem_base, Cfg::ACC_STRIDE, ew, lane,
+                                         smem_u32(epi_stage) + ew * p.epi_nbuf * p.epi_set_bytes, ld_bar + ew * EPI_MAX_NBUF,
+                                         smem_u32(epi_vec) + ew * 1024, tfull_bar, tempty_bar, blockIdx.x, gridDim.x, num_units, 0);
+    } else {
+      const int q = ew & 3;    // == warp % 4: the TMEM lane quarter this warp may read
+      const int ch = ew >> 2;  // even / odd 32-column chunks of the tile
+      int it = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+        const int tile = unit / p.splits;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m0 = (tile / p.num_n_tiles) * BM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
+        const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
 #ifndef TDM_DBG_NOEPI
-      gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
+        gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
 #endif
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      }
     }
     if (lane == 0) tma_store_wait_all();  // the staging tiles must outlive the bulk stores that read them
   }
@@ -420,31 +766,30 @@ struct Gemm2Cfg {
   static constexpr int A_BYTES = BM * BK * 2;        // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * BK * 2;  // this CTA's half of the N extent
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 5 : (BN >= 192 ? 6 : 7);
   static constexpr int ACC_STRIDE = (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_SMEM_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory limit of sm_100");
 };
 
-template <int BN>
+template <int BN, bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                   const __grid_constant__ CUtensorMap tmC16, const __grid_constant__ CUtensorMap tmC32,
-                  const GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmAct,
+                  const __grid_constant__ CUtensorMap tmPre, const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
+  const int STAGES = p.stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-byte aligned: stages are multiples of 4 KB... see assert
-  static_assert((STAGES * Cfg::STAGE_BYTES) % 1024 == 0, "epilogue staging must stay 1024-byte aligned");
-  float* epi_vec = reinterpret_cast<float*>(epi_stage + EPI_WARPS * EPI_STAGE_WARP);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + EPI_SMEM_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  static_assert(Cfg::STAGE_BYTES % 1024 == 0, "epilogue staging must stay 1024-byte aligned");
+  uint8_t* epi_stage = smem + STAGES * Cfg::STAGE_BYTES;
+  float* epi_vec = reinterpret_cast<float*>(epi_stage + p.epi_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + p.epi_bytes + EPI_VEC_BYTES);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tfull_bar = empty_bar + MAX_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ld_bar = tempty_bar + 2;  // [EPI_WARPS][EPI_MAX_NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ld_bar + EPI_WARPS * EPI_MAX_NBUF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -464,6 +809,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tma_prefetch_desc(&tmB2);
     }
   }
+  if (FAST && warp == 4 && lane == 0) {
+    if (p.out_bf16) tma_prefetch_desc(&tmC16);
+    if (p.out_f32) tma_prefetch_desc(&tmC32);
+    if (p.res) tma_prefetch_desc(&tmRes);
+    if (p.act_in) tma_prefetch_desc(&tmAct);
+    if (p.pre_out) tma_prefetch_desc(&tmPre);
+  }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -473,6 +825,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], 2 * EPI_WARPS);
     }
+    if constexpr (FAST)
+      for (int s = 0; s < EPI_WARPS * EPI_MAX_NBUF; ++s) mbar_init(&ld_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
@@ -498,8 +852,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sA = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sB = sA + Cfg::A_BYTES;
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const uint32_t fb = smem_u32(&full_bar[stage]) & PEER_BIT_MASK;  // the leader's barrier, from either CTA
+#ifdef TDM_DBG_NOTMA
+          if (leader) mbar_arrive(&full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          continue;
+#endif
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
           const CUtensorMap* mA = &tmA;
           const CUtensorMap* mB = &tmB;
           int ka = kb * BK, kbb = kb * BK;
@@ -556,8 +915,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t da = a_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
             const uint64_t db = b_desc0 + uint64_t(stage * (Cfg::STAGE_BYTES >> 4));
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+#ifndef TDM_DBG_NOMMA
               umma_bf16_2cta(tmem_d, da + uint64_t(k * a_kstep), db + uint64_t(k * b_kstep), idesc, (kb > kb0) || (k != 0));
+#endif
+            }
             umma_commit_2cta(&empty_bar[stage]);  // frees the stage in BOTH CTAs when these MMAs retire
           }
           __syncwarp();
@@ -573,23 +935,32 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: each owns its 128 accumulator rows) =====================
     const int ew = warp - 4;
-    const int q = ew & 3;
-    const int ch = ew >> 2;
-    int it = 0;
-    for (int unit = pair; unit < num_units; unit += npairs, ++it) {
-      const int tile = unit / p.splits;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
-      const int n0 = (tile % p.num_n_tiles) * BN;
-      gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
-      gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[as]) & PEER_BIT_MASK);  // the leader's barrier
+    if constexpr (FAST) {
+      const EpiMaps maps = {&tmC16, &tmC32, &tmRes, &tmAct, &tmPre};
+      gemm_epilogue_warp_loop<BN, true>(p, maps, tmem_base, Cfg::ACC_STRIDE, ew, lane,
+                                        smem_u32(epi_stage) + ew * p.epi_nbuf * p.epi_set_bytes, ld_bar + ew * EPI_MAX_NBUF,
+                                        smem_u32(epi_vec) + ew * 1024, tfull_bar, tempty_bar, pair, npairs, num_units, (int)rank);
+    } else {
+      const int q = ew & 3;
+      const int ch = ew >> 2;
+      int it = 0;
+      for (int unit = pair; unit < num_units; unit += npairs, ++it) {
+        const int tile = unit / p.splits;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % p.num_n_tiles) * BN;
+        gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
+        const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#ifndef TDM_DBG_NOEPI
+        gemm_epilogue_rows<BN>(p, &tmC16, &tmC32, taddr, m0, n0, q, ch, lane, epi_stage + ew * EPI_STAGE_WARP, epi_vec, as);
+#endif
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(smem_u32(&tempty_bar[as]) & PEER_BIT_MASK);  // the leader's barrier
+      }
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -627,7 +998,7 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, lon
 
 template <int BN, bool PAIR>
 static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
-  constexpr int SMEM = PAIR ? Gemm2Cfg<BN>::SMEM_BYTES : GemmCfg<BN>::SMEM_BYTES;
+  constexpr int STAGE_BYTES = PAIR ? Gemm2Cfg<BN>::STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
   constexpr int TILE_M = PAIR ? 2 * BM : BM;   // rows of one work unit
   constexpr int BOX_N = PAIR ? BN / 2 : BN;    // B rows one CTA stages per k-block
   CUtensorMap tmA, tmB, tmA2, tmB2;
@@ -670,7 +1041,6 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   p.res = g->res; p.ld_res = g->ld_res;
   p.out_f32 = g->out_f32; p.ld_out_f32 = g->ld_out_f32;
   p.out_bf16 = (bf16*)g->out_bf16; p.ld_out_bf16 = g->ld_out_bf16;
-  p.gate_uniform = (p.rows_per_gate % BM) == 0;
   // Split-K: only for pure accumulation (dW += dy^T x style: res aliases out_f32, nothing else in the epilogue),
   // when the output has too few tiles to fill the machine and K is long.  Partial sums are red.add'ed into
   // out_f32, so the existing contents play the role of `res`.
@@ -693,25 +1063,78 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
     }
   }
 
-  static bool attr_set = false;  // per template instantiation
+  // Epilogue flavour and shared-memory plan.  The streaming (FAST) epilogue moves every epilogue tensor by TMA; the
+  // generic one keeps the rare features: split-K reductions, the row-modulo residual (pos_embed), the unrounded
+  // pre-activation copy and gates that change inside a 128-row tile.
+  p.gate_uniform = (p.rows_per_gate % BM) == 0;
+  if (!(g->act == TDM_ACT_GELU_TANH_BWD || g->act == TDM_ACT_SILU_BWD)) p.act_in = nullptr;  // unused otherwise
+  static const bool force_generic = getenv("TDM_B200_GEMM_GENERIC") && atoi(getenv("TDM_B200_GEMM_GENERIC")) != 0;
+  const bool fast = !force_generic && p.splits == 1 && g->res_row_mod == 0 && !g->pre_out_f32 && (!g->gate || p.gate_uniform) &&
+                    (((uintptr_t)g->res | (uintptr_t)p.act_in | (uintptr_t)g->pre_out) & 15) == 0;
+  constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - EPI_VEC_BYTES;
+  CUtensorMap tmRes = tmA, tmAct = tmA, tmPre = tmA;
+  p.epi_nbuf = 1; p.epi_set_bytes = 0; p.epi_off_h0 = p.epi_off_h1 = 0; p.epi_in_bytes = 0; p.epi_feat_slot = -1;
+  if (fast) {
+    const bool need_f = g->res || g->out_f32, need_h0 = p.act_in || g->out_bf16, need_h1 = g->pre_out != nullptr;
+    p.epi_off_h0 = need_f ? EPI_STAGE_F32 : 0;
+    p.epi_off_h1 = p.epi_off_h0 + (need_h0 ? EPI_STAGE_BF16 : 0);
+    p.epi_set_bytes = (p.epi_off_h1 + (need_h1 ? EPI_STAGE_BF16 : 0) + 1023) & ~1023;
+    p.epi_in_bytes = (g->res ? EPI_STAGE_F32 : 0) + (p.act_in ? EPI_STAGE_BF16 : 0);
+    // three sets per warp when something is loaded (load one chunk ahead without waiting for the youngest store), as
+    // long as the operand ring keeps >= 4 stages; two otherwise
+    p.epi_nbuf = 2;
+    if (p.epi_in_bytes > 0 && (AVAIL - EPI_WARPS * 3 * p.epi_set_bytes) / STAGE_BYTES >= 4) p.epi_nbuf = 3;
+    p.epi_bytes = EPI_WARPS * p.epi_nbuf * p.epi_set_bytes;
+    const bool plain_act = g->act == TDM_ACT_NONE || g->act == TDM_ACT_GELU_TANH || g->act == TDM_ACT_GELU_TANH_BWD;
+    const int feat = (g->out_bf16 ? EF_OUT16 : 0) | (g->out_f32 ? EF_OUT32 : 0) | (g->res ? EF_RES : 0) | (g->gate ? EF_GATE : 0) |
+                     (g->pre_out ? EF_PRE : 0) | (g->act == TDM_ACT_GELU_TANH ? EF_GELU : 0) |
+                     (g->act == TDM_ACT_GELU_TANH_BWD ? EF_GELU_BWD : 0);
+    static const bool force_dyn = getenv("TDM_B200_GEMM_DYN") && atoi(getenv("TDM_B200_GEMM_DYN")) != 0;
+    p.epi_feat_slot = (plain_act && !force_dyn) ? epi_feat_slot(feat) : -1;
+    const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+    const uint32_t box[2] = {32, 32};
+    if (g->res) {
+      const uint64_t st[1] = {(uint64_t)g->ld_res * 4};
+      if ((rc = make_tma_typed(&tmRes, g->res, 1, 2, dims, st, box, TMA_SWZ_128))) return rc;
+    }
+    if (p.act_in) {
+      const uint64_t st[1] = {(uint64_t)g->ld_act * 2};
+      if ((rc = make_tma_typed(&tmAct, p.act_in, 0, 2, dims, st, box, TMA_SWZ_64))) return rc;
+    }
+    if (g->pre_out) {
+      const uint64_t st[1] = {(uint64_t)g->ld_pre * 2};
+      if ((rc = make_tma_typed(&tmPre, g->pre_out, 0, 2, dims, st, box, TMA_SWZ_64))) return rc;
+    }
+  } else {
+    p.epi_bytes = EPI_GENERIC_BYTES;
+  }
+  p.stages = (AVAIL - p.epi_bytes) / STAGE_BYTES;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  if (p.stages < 2) return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: no shared memory left for the operand ring (tile_n=%d)", BN);
+  const int smem = gemm_smem_bytes(p.stages, STAGE_BYTES, p.epi_bytes);
+
   const int units = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int sms = num_sms();
+  static bool attr_done[2] = {false, false};  // per template instantiation: [generic, fast]
+  auto launch = [&](auto kernel, int grid) -> int {
+    bool& attr_set = attr_done[fast ? 1 : 0];
+    if (!attr_set) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+      attr_set = true;
+    }
+    ::tdm::count_launch();
+    TDM_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, tmRes, tmAct,
+                              tmPre, p));
+    return TDM_OK;
+  };
   if constexpr (PAIR) {
-    if (!attr_set) {
-      TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-      attr_set = true;
-    }
     const int pairs = units < sms / 2 ? units : sms / 2;
-    ::tdm::count_launch();
-    TDM_CHECK_CUDA(launch_pdl(gemm2_bf16_kernel<BN>, dim3(2 * pairs), dim3(GEMM_THREADS), SMEM, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, p));
+    if (fast) { if ((rc = launch(gemm2_bf16_kernel<BN, true>, 2 * pairs))) return rc; }
+    else { if ((rc = launch(gemm2_bf16_kernel<BN, false>, 2 * pairs))) return rc; }
   } else {
-    if (!attr_set) {
-      TDM_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-      attr_set = true;
-    }
     const int grid = units < sms ? units : sms;
-    ::tdm::count_launch();
-    TDM_CHECK_CUDA(launch_pdl(gemm_bf16_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), SMEM, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, p));
+    if (fast) { if ((rc = launch(gemm_bf16_kernel<BN, true>, grid))) return rc; }
+    else { if ((rc = launch(gemm_bf16_kernel<BN, false>, grid))) return rc; }
   }
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
@@ -720,6 +1143,19 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
 }  // namespace tdm
 
 using namespace tdm;
+
+#ifdef TDM_DBG_TIMING
+extern "C" int tdm_dbg_read(long long* out, int max_pairs) {
+  int n = max_pairs < 4096 ? max_pairs : 4096;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, tdm_dbg_times, sizeof(long long) * n);
+  static uint32_t zeros[32 * 8];
+  cudaMemcpyToSymbol(tdm_dbg_cj, zeros, sizeof(zeros));
+  static long long zt[8192];
+  cudaMemcpyToSymbol(tdm_dbg_times, zt, sizeof(zt));
+  return n;
+}
+#endif
 
 extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   TDM_REQUIRE(g != nullptr, "tdm_gemm_bf16: null descriptor");
