@@ -10,6 +10,7 @@
 // head_dim 72 is not a multiple of 64: every tile is loaded as ceil(d/64) 128-byte-swizzled column
 // chunks straight from the [tokens, heads*d] activation matrix with a 4-D tensor map (d, S, H, B);
 // TMA zero-fills columns >= d and rows >= S, so no padded copy of Q/K/V ever exists in HBM.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tdm {
@@ -66,13 +67,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_empty = bars + 2;   // [2]
   uint64_t* s_full = bars + 4;    // [2]
   uint64_t* p_full = bars + 6;
-  uint64_t* pv_done = bars + 7;
+  uint64_t* pv_done = bars + 21;  // [2] by tile parity (see the softmax warps' waits)
   uint64_t* o_free = bars + 8;
   uint64_t* k_full = bars + 9;    // [3]
   uint64_t* v_full = bars + 12;   // [3]
   uint64_t* k_empty = bars + 15;  // [3]  K stage free as soon as Q K^T of the tile retired (a whole tile earlier than V)
   uint64_t* v_empty = bars + 18;  // [3]  V stage free: P V of the tile retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.Sk + ATT_BN - 1) / ATT_BN;
@@ -94,7 +95,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&k_empty[i], 1);
     }
     mbar_init(p_full, 256);
-    mbar_init(pv_done, 1);
+    mbar_init(&pv_done[0], 1);
+    mbar_init(&pv_done[1], 1);
     mbar_init(o_free, 256);
     fence_barrier_init();
   }
@@ -187,7 +189,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int k = 0; k < ATT_BN / 16; ++k)  // 16 keys = 8 packed TMEM columns = 2048 smem bytes per step
           umma_bf16_ts(tmem_O, p_addr + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0);
         umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[g & 1]);
       }
       __syncwarp();
     }
@@ -257,7 +259,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (j == 0) {
           m_used = m_new;
         } else if (__any_sync(0xffffffffu, m_new - m_used > 8.f)) {
-          mbar_wait(pv_done, (g - 1) & 1);  // O must not be rescaled under an in-flight P V
+          // O must not be rescaled under an in-flight P V.  The softmax warps wait for P V only here and at the end of an
+          // item, not every tile, so a single barrier would alias: S(g) ready only implies P V(g-2) retired, and with
+          // P V(g-2).. two phases behind a parity wait passes at once (seen as stale O when the V tiles arrive late).
+          // One barrier per tile parity: its awaited phase is either current or complete, never two behind.
+          mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);
           tc_fence_after();
           const float alpha = ex2_fast(m_used - m_new);
           l_run *= alpha;
@@ -305,7 +311,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       sL[wg * 128 + row] = l_run;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       l_run += sL[(wg ^ 1) * 128 + row];
-      mbar_wait(pv_done, (g - 1) & 1);
+      mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1);  // the item's last P V (the tensor pipe retires in order)
       tc_fence_after();
       const int q = q0 + row;
       const float inv_l = 1.f / l_run;
@@ -393,7 +399,8 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   const long items = (long)((a->Sq + ATT_BM - 1) / ATT_BM) * a->H * a->B;
   const int grid = (int)(items < num_sms() ? items : num_sms());
   ::tdm::count_launch();
-  TDM_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
+  static const bool pdl_attn = !(getenv("TDM_B200_PDL_ATTN") && atoi(getenv("TDM_B200_PDL_ATTN")) == 0);
+  TDM_CHECK_CUDA(launch_pdl_if(pdl_attn, attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -7,6 +7,7 @@
 //   warps 4-7: epilogue      -- tcgen05.ld (thread == accumulator row) -> fused math -> global
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
 // Tails in M, N and K are handled by TMA out-of-bounds zero fill plus predicated stores.
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -264,6 +265,12 @@ __device__ uint32_t tdm_dbg_cj[32 * 8];
 #define DBG_T(tag)
 #endif
 
+__device__ __forceinline__ float ld_global_f32(const float* ptr) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
 struct EpiMaps {
   const CUtensorMap *c16, *c32, *res, *act, *pre;
 };
@@ -496,8 +503,10 @@ __device__ __forceinline__ void gemm_epilogue_warp_loop(const GemmParams& p, con
     for (int k = 0; k < NCH; ++k) {
       const int n = n0_ + ch * 32 + k * 64 + lane;
       const bool ok = n < p.N && ch * 32 + k * 64 < BN;
-      bias_r[k] = (p.bias && ok) ? __ldg(p.bias + n) : 0.f;
-      gate_r[k] = (gate_tile && ok) ? __ldg(gate_tile + n) : 1.f;
+      // plain (coherent, ordered) loads: the gate rows are written by the kernel just before this one, and an
+      // invariant (__ldg) load may be hoisted above griddepcontrol.wait by the compiler
+      bias_r[k] = (p.bias && ok) ? ld_global_f32(p.bias + n) : 0.f;
+      gate_r[k] = (gate_tile && ok) ? ld_global_f32(gate_tile + n) : 1.f;
     }
   };
   uint32_t buf = 0, ph = 0;
@@ -996,6 +1005,30 @@ static int make_operand_map(CUtensorMap* map, const void* ptr, int mn_major, lon
   return make_tma_bf16(map, ptr, 2, dims, strides, box, TMA_SWZ_128);
 }
 
+// Split-K applies only to pure accumulation (dW += dy^T x style: res aliases out_f32, nothing else in the epilogue):
+// partial sums are red.add'ed into out_f32, so the existing contents play the role of `res`.
+static bool gemm_acc_only(const TdmGemm* g) {
+  return g->res && g->res == g->out_f32 && g->ld_res == g->ld_out_f32 && !g->bias && !g->gate && g->act == TDM_ACT_NONE &&
+         !g->out_bf16 && !g->pre_out && !g->pre_out_f32 && g->res_row_mod == 0 && g->K2 <= 0;
+}
+// Split factor when the output tiles alone cannot fill the machine and K is long: the s in [1, 6] (>= 8 k-blocks per
+// unit) with the fewest waves per split, ceil(tiles * s / slots) / s; ties go to fewer partial sums to reduce in HBM.
+static int gemm_plan_splits(const TdmGemm* g, int tiles0, int slots) {
+  const int nk = (g->K + BK - 1) / BK;
+  if (g->split_k > 1) return g->split_k < nk ? g->split_k : nk;
+  if (g->split_k == 1 || !gemm_acc_only(g) || tiles0 >= slots || nk < 16) return 1;
+  int best = 1;
+  double best_c = 1e30;
+  for (int sp = 1; sp <= 6 && sp <= nk / 8; ++sp) {
+    const double c = double((tiles0 * sp + slots - 1) / slots) / sp;
+    if (c < best_c - 1e-9) {
+      best_c = c;
+      best = sp;
+    }
+  }
+  return best;
+}
+
 template <int BN, bool PAIR>
 static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   constexpr int STAGE_BYTES = PAIR ? Gemm2Cfg<BN>::STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
@@ -1041,27 +1074,9 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   p.res = g->res; p.ld_res = g->ld_res;
   p.out_f32 = g->out_f32; p.ld_out_f32 = g->ld_out_f32;
   p.out_bf16 = (bf16*)g->out_bf16; p.ld_out_bf16 = g->ld_out_bf16;
-  // Split-K: only for pure accumulation (dW += dy^T x style: res aliases out_f32, nothing else in the epilogue),
-  // when the output has too few tiles to fill the machine and K is long.  Partial sums are red.add'ed into
-  // out_f32, so the existing contents play the role of `res`.
-  p.splits = 1;
-  {
-    const bool acc_only = g->res && g->res == g->out_f32 && g->ld_res == g->ld_out_f32 && !g->bias && !g->gate &&
-                          g->act == TDM_ACT_NONE && !g->out_bf16 && !g->pre_out && !g->pre_out_f32 &&
-                          g->res_row_mod == 0 && p.K2 == 0;
-    const int tiles0 = p.num_m_tiles * p.num_n_tiles;
-    const int nk = (p.K + BK - 1) / BK;
-    int want = g->split_k;
-    if (want == 0 && acc_only && tiles0 < num_sms() && nk >= 16) {  // the output tiles alone cannot fill the machine
-      want = (num_sms() + tiles0 / 2) / tiles0;  // ~1 work unit per SM (1152x1152 wgrad: 54 tiles x 3 -> 39 vs 54 us)
-      if (want > nk / 8) want = nk / 8;          // keep >= 8 k-blocks per unit: fewer partial sums to reduce in HBM
-    }
-    if (want > 1) {
-      if (!acc_only) return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: split_k needs an accumulate-only epilogue (res == out_f32)");
-      if (want > nk) want = nk;
-      p.splits = want;
-    }
-  }
+  if (g->split_k > 1 && !gemm_acc_only(g))
+    return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: split_k needs an accumulate-only epilogue (res == out_f32)");
+  p.splits = gemm_plan_splits(g, p.num_m_tiles * p.num_n_tiles, PAIR ? num_sms() / 2 : num_sms());
 
   // Epilogue flavour and shared-memory plan.  The streaming (FAST) epilogue moves every epilogue tensor by TMA; the
   // generic one keeps the rare features: split-K reductions, the row-modulo residual (pos_embed), the unrounded
@@ -1123,8 +1138,9 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
       attr_set = true;
     }
     ::tdm::count_launch();
-    TDM_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32, tmRes, tmAct,
-                              tmPre, p));
+    static const bool pdl_gemm = !(getenv("TDM_B200_PDL_GEMM") && atoi(getenv("TDM_B200_PDL_GEMM")) == 0);
+    TDM_CHECK_CUDA(launch_pdl_if(pdl_gemm, kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, tmA, tmB, tmA2, tmB2, tmC16, tmC32,
+                                 tmRes, tmAct, tmPre, p));
     return TDM_OK;
   };
   if constexpr (PAIR) {
@@ -1181,23 +1197,27 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
                   (!g->pre_out_f32 || g->ld_pre_f32 % 4 == 0) &&
                   (!g->act_in || g->ld_act % 8 == 0) && (!g->gate || g->gate_stride % 4 == 0),
               "tdm_gemm_bf16: epilogue leading dimensions must keep 16-byte alignment");
-  // Tile / mode choice, calibrated on B200 measurements (scripts/bench_kernels.py, profiles/): the mainloop of a
-  // 128 x BN tile costs ~ (BN + 64) per k-block (wider tiles amortise the A operand and the per-tile ramp), times the
-  // number of waves over the SMs (single CTA) or SM pairs.  The CTA-pair kernel only pays off for long-K, large
-  // problems with K-major operands (8192^3: 1424 vs 1280 TFLOP/s); at the model's K = 1152 the two are equal, so
-  // the simpler single-CTA kernel is the default there.
+  // Tile / mode choice, calibrated on B200 measurements under the sustained power cap (scripts/bench_gemm_one.py,
+  // profiles/): the mainloop is bound by the L2 -> shared-memory operand stream, so a tile costs its operand rows per
+  // k-block -- (BN + 128) for a CTA pair (each CTA stages 128 rows of A and BN / 2 rows of B for 128 x BN outputs... per
+  // SM: (BN + 256) / 2 rows per 128 x BN), 1.3 x (BN + 64) for a single CTA -- times the number of waves over the SM
+  // pairs / SMs.  8192 x {1152, 3456, 4608} x 1152: pair-192 26.1 us, pair-256 62.7 / 73.7 us against 27.0 / 69.4 /
+  // 83.9 us single-CTA (cuBLAS in the same loop: 25.7 / 57.4 / 73.7 us).
   const int sms = num_sms();
   int bn = g->tile_n;
   int pair = g->cta_pair;  // 0 choose, 1 single CTA, 2 CTA pair
+  static const int env_pair = getenv("TDM_B200_GEMM_PAIR") ? atoi(getenv("TDM_B200_GEMM_PAIR")) : 0;  // debugging aid
+  if (pair == 0 && env_pair == 1) pair = 1;
   TDM_REQUIRE(pair >= 0 && pair <= 2, "tdm_gemm_bf16: cta_pair must be 0 (choose), 1 (single) or 2 (pair)");
-  if (pair == 0)  // measured (profiles/r01_kernel_microbench): FF2 8192x1152x4608 82 vs 91 us, 8192^3 753 vs 964 us
-    pair = (g->M >= 1024 && (g->K >= 2048 || g->N >= 4096) && !g->a_mn_major && !g->b_mn_major && g->seg_n == 0) ? 2 : 1;
   auto cost = [&](int b, bool pr) {
-    const long mt = pr ? (g->M + 255) / 256 : (g->M + 127) / 128;
-    const long t = mt * ((g->N + b - 1) / b);
-    const long slots = pr ? sms / 2 : sms;
-    const long waves = (t + slots - 1) / slots;
-    return double(waves) * double(b + 64);
+    const int mt = pr ? (g->M + 255) / 256 : (g->M + 127) / 128;
+    const int nt = (g->N + b - 1) / b;
+    const int slots = pr ? sms / 2 : sms;
+    const int sp = gemm_plan_splits(g, mt * nt, slots);
+    // a ragged last column tile fetches (and so costs) only its valid part: count it as a fraction of a tile
+    const double units = double(mt) * (double(g->N) / b) * sp;
+    const double waves = ceil(units / slots - 0.02);
+    return (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.3) / sp;
   };
   auto allowed = [&](int b, bool pr) {
     if (g->seg_n > 0 && g->seg_n % b != 0) return false;
@@ -1206,7 +1226,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
     return true;
   };
   if (bn == 0 || pair == 0) {
-    const int cands[4] = {192, 256, 128, 64};  // ties go to 192: measured faster than 256 at N = 1152 / 3456
+    const int cands[4] = {256, 192, 128, 64};
     double best = 1e30;
     int best_bn = 0, best_pair = 1;
     for (int pm = 2; pm >= 1; --pm) {
@@ -1216,7 +1236,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
         if (bn != 0 && b != bn) continue;
         if (!allowed(b, pm == 2)) continue;
         const double c = cost(b, pm == 2);
-        if (c < best * 0.97) {  // prefer the earlier candidate unless a later one is clearly better
+        if (c < best * 0.97) {  // prefer the earlier (wider, paired) candidate unless a later one is clearly better
           best = c;
           best_bn = b;
           best_pair = pm;

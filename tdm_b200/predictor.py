@@ -71,20 +71,49 @@ class Predictor:
             c, m = c[:1].expand(B, *c.shape[1:]), m[:1].expand(B, *m.shape[1:])
         return c, m
 
+    # The reference evaluates the conditional and the unconditional branch of classifier-free guidance as two model
+    # calls (predictor.py:33-39).  No op of the DiT couples samples, so under no_grad both branches run here as ONE
+    # call on the stacked batch [cond; uncond] (2B rows per GEMM: better tile/wave efficiency, half the launches);
+    # the per-sample results are bit-identical to the two separate calls (tests/test_iteration_gpu.py).
+    batch_cfg = True
+
+    def _predict_pair(self, score_model, x, t, ehs, mask):
+        if not hasattr(score_model, "_forward_impl") or ehs is None or mask is None:
+            return None
+        B = x.shape[0]
+        uc, um = self._uncond(B)
+        if uc.shape[1:] != ehs.shape[1:] or um.shape[1:] != mask.shape[1:]:
+            return None
+        t = t.expand(B) if t.dim() == 0 else t
+        x2 = torch.cat([x, x])
+        t2 = torch.cat([t, t])
+        e2 = torch.cat([ehs, uc.to(ehs.dtype)])
+        m2 = torch.cat([mask, um.to(mask.dtype)])
+        out = score_model(x2, timestep=t2, added_cond_kwargs=self.added_cond_kwargs, encoder_hidden_states=e2,
+                          encoder_attention_mask=m2, return_dict=False)[0]
+        return out[:B], out[B:]
+
     def predict(self, score_model, noisy_samples, timesteps, encoder_hidden_states, prompt_attention_mask, cfg=None,
                 steps=1, return_double=False, timestep_cond=None, return_uncond=False):
         """predictor.py:30-74.  `return_uncond` (extension, default off) appends the unconditional x0 estimate to
         the `return_double` tuple: the quantity main.py:508 names `sd_latents_uncond`."""
         pred_type = self.noise_scheduler.config.prediction_type
         for _ in range(steps):
-            out_c = score_model(noisy_samples, timestep=timesteps, added_cond_kwargs=self.added_cond_kwargs,
-                                encoder_hidden_states=encoder_hidden_states,
-                                encoder_attention_mask=prompt_attention_mask, return_dict=False)[0]
             t_long = timesteps.long()
+            pair = None
+            if cfg is not None and self.batch_cfg and not torch.is_grad_enabled():
+                pair = self._predict_pair(score_model, noisy_samples, timesteps, encoder_hidden_states, prompt_attention_mask)
+            if pair is not None:
+                out_c, out_u = pair
+            else:
+                out_c = score_model(noisy_samples, timestep=timesteps, added_cond_kwargs=self.added_cond_kwargs,
+                                    encoder_hidden_states=encoder_hidden_states,
+                                    encoder_attention_mask=prompt_attention_mask, return_dict=False)[0]
             if cfg is not None:
-                uc, um = self._uncond(noisy_samples.shape[0])
-                out_u = score_model(noisy_samples, timestep=timesteps, added_cond_kwargs=self.added_cond_kwargs,
-                                    encoder_hidden_states=uc, encoder_attention_mask=um, return_dict=False)[0]
+                if pair is None:
+                    uc, um = self._uncond(noisy_samples.shape[0])
+                    out_u = score_model(noisy_samples, timestep=timesteps, added_cond_kwargs=self.added_cond_kwargs,
+                                        encoder_hidden_states=uc, encoder_attention_mask=um, return_dict=False)[0]
                 score_pred_cfg, pred_latents = _step(out_c, out_u, noisy_samples, t_long, self.alpha_schedule,
                                                      self.sigma_schedule, cfg, pred_type)       # predictor.py:42-49
                 score_pred, pred_latents_nocfg = _step(out_c, None, noisy_samples, t_long, self.alpha_schedule,
