@@ -18,9 +18,9 @@ def wgrad(tokens, n_out, k_in):
     x = [torch.randn(tokens, k_in, device="cuda").bfloat16() for _ in range(NB)]
     dw = torch.zeros(n_out, k_in, device="cuda")
     row = {"kind": "wgrad", "tokens": tokens, "n_out": n_out, "k_in": k_in}
-    for name, tn, pr in (("auto", 0, 0), ("s192", 192, 1), ("s256", 256, 1), ("p256", 256, 2), ("p128", 128, 2), ("auto2", 0, 0)):
+    for name, tn, pr, sk in (("auto", 0, 0, 0), ("s192", 192, 1, 0), ("s192_1", 192, 1, 1), ("p256", 256, 2, 0), ("p256_1", 256, 2, 1), ("p128", 128, 2, 0), ("auto2", 0, 0, 0)):
         try:
-            us, mhz = timeit(lambda i: ops.gemm(dy[i % NB], x[i % NB], a_mn_major=True, b_mn_major=True, res=dw, out_f32=dw, tile_n=tn, cta_pair=pr))
+            us, mhz = timeit(lambda i: ops.gemm(dy[i % NB], x[i % NB], a_mn_major=True, b_mn_major=True, res=dw, out_f32=dw, tile_n=tn, cta_pair=pr, split_k=sk))
             row[name] = [round(us, 1), mhz]
         except Exception as e:
             row[name] = str(e)[-60:]

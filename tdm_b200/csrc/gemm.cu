@@ -1016,7 +1016,12 @@ static bool gemm_acc_only(const TdmGemm* g) {
 static int gemm_plan_splits(const TdmGemm* g, int tiles0, int slots) {
   const int nk = (g->K + BK - 1) / BK;
   if (g->split_k > 1) return g->split_k < nk ? g->split_k : nk;
-  if (g->split_k == 1 || !gemm_acc_only(g) || tiles0 >= slots || nk < 16) return 1;
+  if (g->split_k == 1 || !gemm_acc_only(g) || nk < 16) return 1;
+  if (tiles0 >= slots) {  // enough tiles: halve K only to repair a badly filled last wave (2.2 waves -> 3 half waves)
+    const int w1 = (tiles0 + slots - 1) / slots;
+    const double w2 = double((2 * tiles0 + slots - 1) / slots) / 2.0;
+    return (nk >= 32 && w2 < 0.87 * w1) ? 2 : 1;
+  }
   int best = 1;
   double best_c = 1e30;
   for (int sp = 1; sp <= 6 && sp <= nk / 8; ++sp) {
@@ -1200,7 +1205,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   // Tile / mode choice, calibrated on B200 measurements under the sustained power cap (scripts/bench_gemm_one.py,
   // profiles/): the mainloop is bound by the L2 -> shared-memory operand stream, so a tile costs its operand rows per
   // k-block -- (BN + 128) for a CTA pair (each CTA stages 128 rows of A and BN / 2 rows of B for 128 x BN outputs... per
-  // SM: (BN + 256) / 2 rows per 128 x BN), 1.3 x (BN + 64) for a single CTA -- times the number of waves over the SM
+  // SM: (BN + 256) / 2 rows per 128 x BN), 1.5 x (BN + 64) for a single CTA -- times the number of waves over the SM
   // pairs / SMs.  8192 x {1152, 3456, 4608} x 1152: pair-192 26.1 us, pair-256 62.7 / 73.7 us against 27.0 / 69.4 /
   // 83.9 us single-CTA (cuBLAS in the same loop: 25.7 / 57.4 / 73.7 us).
   const int sms = num_sms();
@@ -1217,7 +1222,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
     // a ragged last column tile fetches (and so costs) only its valid part: count it as a fraction of a tile
     const double units = double(mt) * (double(g->N) / b) * sp;
     const double waves = ceil(units / slots - 0.02);
-    return (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.3) / sp;
+    return (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.5) / sp;
   };
   auto allowed = [&](int b, bool pr) {
     if (g->seg_n > 0 && g->seg_n % b != 0) return false;
