@@ -197,7 +197,7 @@ def run_reference(args):
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def gemm_roofline(cfg, B, peaks, iters=20):
-    """Live timing of the dominant kernel (gemm_bf16_kernel) on the block's forward GEMM shapes, CUDA events on
+    """Live timing of the dominant kernel (gemm2_bf16_kernel, the CTA-pair GEMM) on the block's forward GEMM shapes, CUDA events on
     the launching stream; achieved = algorithmic FLOPs / time."""
     from tdm_b200 import ops
     D = cfg["num_attention_heads"] * cfg["attention_head_dim"]
@@ -222,12 +222,13 @@ def gemm_roofline(cfg, B, peaks, iters=20):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     ach = flops / (ms * 1e-3) / 1e12
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_v4_summary.txt):
-    # QKV shape 8192x3456x1152, dram__bytes_read.sum + dram__bytes_write.sum = 26.92 + 8.54 MB (algorithmic operand +
-    # output bytes 83.5 MB: the bf16 output is still in the 126 MB L2 when the kernel ends, nothing is re-read).
-    return {"bound": "tensor", "kernel": "gemm_bf16_kernel<192|256> (tcgen05/TMEM/TMA, TMA-store epilogue), the 6 forward GEMM shapes of one DiT block at M=%d" % M,
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_full_v9_summary.txt):
+    # FF1 shape 8192x4608x1152 (bias + GELU-tanh, bf16 out), dram__bytes_read.sum + dram__bytes_write.sum = 29.59 + 31.31 MB
+    # (algorithmic operand + output bytes 105 MB: part of the bf16 output is still in the 126 MB L2 when the kernel ends,
+    # nothing is re-read).
+    return {"bound": "tensor", "kernel": "gemm2_bf16_kernel<256|192, fast> (CTA-pair tcgen05/TMEM/TMA GEMM, streaming TMA epilogue; 51 % of the iteration), the 6 forward GEMM shapes of one DiT block at M=%d" % M,
             "achieved": ach, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": ach / peaks["burst"],
-            "traffic": {"bytes_per_launch": 35.46e6, "shape": "8192x3456x1152 (QKV)", "source": "ncu --set full, profiles/r01_ncu_full_v4_summary.txt"},
+            "traffic": {"bytes_per_launch": 60.9e6, "shape": "8192x4608x1152 (FF1, bias + GELU-tanh)", "source": "ncu --set full, profiles/r01_ncu_full_v9_summary.txt"},
             "peak_source": peaks["source"] + ", burst figure (kernel timed alone)", "launches_timed": iters * len(shapes),
             "avg_launch_us": ms * 1e3 / len(shapes)}
 
