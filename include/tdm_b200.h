@@ -100,6 +100,9 @@ typedef struct TdmGemm {
   int32_t tile_n;  /* 0 = choose; else 64/128/192/256 */
   int32_t split_k; /* 0 = choose; >1 forces split-K (accumulate-only epilogues: res == out_f32, nothing else) */
   int32_t cta_pair; /* 0 = choose; 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per 256-row tile */
+  int32_t epilogue; /* 0 = choose; 1 = generic epilogue (direct loads / stores); 2 = streaming TMA epilogue with the
+                       run-time tested code; 3 = streaming, feature-specialised instance when one exists (same results,
+                       bit for bit: tests/test_gemm_gpu.py) */
 } TdmGemm;
 
 int tdm_gemm_bf16(const TdmGemm* g, void* stream);

@@ -1089,8 +1089,12 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   p.gate_uniform = (p.rows_per_gate % BM) == 0;
   if (!(g->act == TDM_ACT_GELU_TANH_BWD || g->act == TDM_ACT_SILU_BWD)) p.act_in = nullptr;  // unused otherwise
   static const bool force_generic = getenv("TDM_B200_GEMM_GENERIC") && atoi(getenv("TDM_B200_GEMM_GENERIC")) != 0;
-  const bool fast = !force_generic && p.splits == 1 && g->res_row_mod == 0 && !g->pre_out_f32 && (!g->gate || p.gate_uniform) &&
+  const bool fast_ok = p.splits == 1 && g->res_row_mod == 0 && !g->pre_out_f32 && (!g->gate || p.gate_uniform) &&
                     (((uintptr_t)g->res | (uintptr_t)p.act_in | (uintptr_t)g->pre_out) & 15) == 0;
+  if (g->epilogue >= 2 && !fast_ok)
+    return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: the streaming epilogue does not cover this call (split-K, res_row_mod, pre_out_f32, "
+                                      "a gate that changes inside a tile, or unaligned epilogue tensors)");
+  const bool fast = fast_ok && g->epilogue != 1 && !(force_generic && g->epilogue == 0);
   constexpr int AVAIL = SMEM_LIMIT - 1024 - BAR_BYTES - EPI_VEC_BYTES;
   CUtensorMap tmRes = tmA, tmAct = tmA, tmPre = tmA;
   p.epi_nbuf = 1; p.epi_set_bytes = 0; p.epi_off_h0 = p.epi_off_h1 = 0; p.epi_in_bytes = 0; p.epi_feat_slot = -1;
@@ -1110,7 +1114,7 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
                      (g->pre_out ? EF_PRE : 0) | (g->act == TDM_ACT_GELU_TANH ? EF_GELU : 0) |
                      (g->act == TDM_ACT_GELU_TANH_BWD ? EF_GELU_BWD : 0);
     static const bool force_dyn = getenv("TDM_B200_GEMM_DYN") && atoi(getenv("TDM_B200_GEMM_DYN")) != 0;
-    p.epi_feat_slot = (plain_act && !force_dyn) ? epi_feat_slot(feat) : -1;
+    p.epi_feat_slot = (plain_act && g->epilogue != 2 && !(force_dyn && g->epilogue == 0)) ? epi_feat_slot(feat) : -1;
     const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
     const uint32_t box[2] = {32, 32};
     if (g->res) {
@@ -1213,6 +1217,7 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   int pair = g->cta_pair;  // 0 choose, 1 single CTA, 2 CTA pair
   static const int env_pair = getenv("TDM_B200_GEMM_PAIR") ? atoi(getenv("TDM_B200_GEMM_PAIR")) : 0;  // debugging aid
   if (pair == 0 && env_pair == 1) pair = 1;
+  TDM_REQUIRE(g->epilogue >= 0 && g->epilogue <= 3, "tdm_gemm_bf16: epilogue must be 0 (choose), 1 (generic), 2 or 3 (streaming)");
   TDM_REQUIRE(pair >= 0 && pair <= 2, "tdm_gemm_bf16: cta_pair must be 0 (choose), 1 (single) or 2 (pair)");
   auto cost = [&](int b, bool pr) {
     const int mt = pr ? (g->M + 255) / 256 : (g->M + 127) / 128;

@@ -28,7 +28,7 @@ def _req(t, dtype, name):
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a2=None, b2=None, seg_n=0, seg_k2=0,
          alpha=1.0, bias=None, act=ACT_NONE, act_in=None, pre_out=None, pre_out_f32=None, gate=None,
-         rows_per_gate=1, res=None, res_row_mod=0, out_f32=None, out_bf16=None, tile_n=0, split_k=0, cta_pair=0):
+         rows_per_gate=1, res=None, res_row_mod=0, out_f32=None, out_bf16=None, tile_n=0, split_k=0, cta_pair=0, epilogue=0):
     """C[M,N] = alpha*(A.B^T + A2.B2^T) with the fused epilogue of include/tdm_b200.h (TdmGemm).
 
     a: [M,K] (or [K,M] when a_mn_major); b: [N,K] (or [K,N] when b_mn_major); 2-D views with unit
@@ -75,6 +75,7 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a2=None, b2=None, seg_n=0,
     g.tile_n = tile_n
     g.split_k = split_k
     g.cta_pair = cta_pair
+    g.epilogue = epilogue
     check(_lib.lib().tdm_gemm_bf16(C.byref(g), stream_handle()))
 
 

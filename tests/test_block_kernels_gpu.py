@@ -170,3 +170,33 @@ def test_attention_fwd_bwd(B, H, Sq, Sk, d, cross):
     assert _rel(dv, vf.grad) < 2e-2, "dV"
     assert _rel(dk, kf.grad) < 2e-2, "dK"
     assert _rel(dq, qf.grad) < 2e-2, "dQ"
+
+
+@pytest.mark.parametrize("B,H,S,d", [(2, 16, 1024, 72), (8, 16, 1024, 72)])
+def test_attention_fwd_is_deterministic_with_cold_loads(B, H, S, d):
+    """Regression for the P V completion barrier of attn_fwd_kernel: with one barrier for every tile, a parity wait could
+    pass two phases early when the V tiles arrived late (cold L2 / TLB, programmatic dependent launch) and O was read
+    before the last P V landed -- O changed from run to run while the log-sum-exp stayed the same.  Many launches,
+    L2 flushed in between, several items per CTA: every output must equal the first one bit for bit."""
+    from tdm_b200 import ops
+    D = H * d
+    g = torch.Generator(device="cuda").manual_seed(11)
+    qkv = torch.randn(B, S, 3 * D, device="cuda", generator=g).bfloat16()
+    q, k, v = (qkv[:, :, i * D:(i + 1) * D].view(B, S, H, d) for i in range(3))
+    junk = torch.empty(160 << 20, device="cuda", dtype=torch.uint8)   # larger than the 126 MB L2
+    first_o = first_lse = None
+    for it in range(24):
+        o = torch.empty(B, S, H, d, device="cuda", dtype=torch.bfloat16)
+        lse = torch.empty(B, H, S, device="cuda")
+        junk.zero_()
+        ops.attn_fwd(q, k, v, o, d ** -0.5, lse=lse)
+        ops.attn_fwd(q, k, v, o, d ** -0.5, lse=lse)   # back to back: the second launch overlaps the first one's tail
+        torch.cuda.synchronize()
+        if first_o is None:
+            first_o, first_lse = o, lse
+            ref = F.scaled_dot_product_attention(q.transpose(1, 2).float(), k.transpose(1, 2).float(),
+                                                 v.transpose(1, 2).float()).transpose(1, 2)
+            assert (o.float() - ref).abs().max().item() < 1e-2
+        else:
+            assert torch.equal(o, first_o), f"launch {it}: attention output changed"
+            assert torch.equal(lse, first_lse)

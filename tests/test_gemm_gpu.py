@@ -162,3 +162,56 @@ def test_gemm_rejects_bad_args():
         ops.gemm(a, b, out_f32=torch.empty(64, 60, device="cuda"))  # N % 8 != 0
     with pytest.raises(_lib.TdmError):
         ops.gemm(a, _mk((64, 64)))  # no output
+
+
+_EPI_CASES = {
+    # name: kwargs builder (M, N given) -> the eight feature sets the streaming epilogue is specialised for, plus extras
+    "bf16": lambda t: dict(bias=t["bias"], out_bf16=t["o16"]),
+    "gelu": lambda t: dict(bias=t["bias"], act=1, out_bf16=t["o16"]),
+    "gelu_pre": lambda t: dict(bias=t["bias"], act=1, pre_out=t["pre"], out_bf16=t["o16"]),
+    "gelu_bwd": lambda t: dict(act=2, act_in=t["u"], out_bf16=t["o16"]),
+    "res32": lambda t: dict(bias=t["bias"], res=t["res"], out_f32=t["o32"]),
+    "gate_res32": lambda t: dict(bias=t["bias"], gate=t["gate"], rows_per_gate=t["T"], res=t["res"], out_f32=t["o32"]),
+    "gate_res32_bf16": lambda t: dict(bias=t["bias"], gate=t["gate"], rows_per_gate=t["T"], res=t["res"], out_f32=t["o32"],
+                                      out_bf16=t["o16"]),
+    "merge": lambda t: dict(alpha=0.5, res=t["res"], out_bf16=t["o16"]),
+    "everything": lambda t: dict(bias=t["bias"], act=1, pre_out=t["pre"], gate=t["gate"], rows_per_gate=t["T"], res=t["res"],
+                                 out_f32=t["o32"], out_bf16=t["o16"], alpha=0.5),
+    "silu_bwd_inplace": lambda t: dict(act=4, act_in=t["u"], res=t["o32"], out_f32=t["o32"]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(_EPI_CASES))
+@pytest.mark.parametrize("cta_pair,tile_n", [(1, 64), (1, 192), (2, 128), (2, 256)])
+def test_streaming_epilogue_instances_are_bit_identical(case, cta_pair, tile_n):
+    """The generic epilogue (epilogue=1), the streaming epilogue with run-time tests (2) and its feature-specialised
+    instance (3) must agree bit for bit on every output -- ragged M and N tails included -- and match the fp32 formula."""
+    from tdm_b200 import ops
+    B, T, N, K = 3, 384, 328, 200   # M = 1152 rows (gate uniform per 128-row tile), N tail of 8 columns past 320
+    M = B * T
+    a, w = _mk((M, K), seed=21), _mk((N, K), 0.1, seed=22)
+    base = dict(bias=torch.randn(N, device="cuda"), gate=torch.randn(B, 6 * N, device="cuda")[:, N:2 * N], T=T,
+                res=torch.randn(M, N, device="cuda"), u=_mk((M, N), seed=23))
+    outs = []
+    for mode in (1, 2, 3):
+        t = dict(base, pre=torch.zeros(M, N, device="cuda", dtype=torch.bfloat16), o32=base["res"].clone() * 0.25,
+                 o16=torch.zeros(M, N, device="cuda", dtype=torch.bfloat16))
+        ops.gemm(a, w, tile_n=tile_n, cta_pair=cta_pair, epilogue=mode, **_EPI_CASES[case](t))
+        torch.cuda.synchronize()
+        outs.append((t["pre"], t["o32"], t["o16"]))
+    for mode, o in zip((2, 3), outs[1:]):
+        for name, x, y in zip(("pre_out", "out_f32", "out_bf16"), outs[0], o):
+            assert torch.equal(x, y), f"{case}: epilogue={mode} differs from the generic epilogue in {name}"
+    if case == "gate_res32_bf16":  # one closed-form check of the shared result
+        v = a.float() @ w.float().t() + base["bias"]
+        ref = v * base["gate"].repeat_interleave(T, 0) + base["res"]
+        _close(outs[2][1], ref, 2e-4, "out_f32")
+        _close(outs[2][2], ref, 6e-3, "out_bf16")
+
+
+def test_streaming_epilogue_refuses_what_it_does_not_cover():
+    from tdm_b200 import ops, _lib
+    a, w = _mk((256, 64), seed=1), _mk((128, 64), seed=2)
+    acc = torch.zeros(256, 128, device="cuda")
+    with pytest.raises(_lib.TdmError):
+        ops.gemm(a, w, res=acc[:100], res_row_mod=100, out_f32=acc, epilogue=3)
