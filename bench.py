@@ -226,7 +226,7 @@ def gemm_roofline(cfg, B, peaks, iters=20):
     # FF1 shape 8192x4608x1152 (bias + GELU-tanh, bf16 out), dram__bytes_read.sum + dram__bytes_write.sum = 29.59 + 31.31 MB
     # (algorithmic operand + output bytes 105 MB: part of the bf16 output is still in the 126 MB L2 when the kernel ends,
     # nothing is re-read).
-    return {"bound": "tensor", "kernel": "gemm2_bf16_kernel<256|192, fast> (CTA-pair tcgen05/TMEM/TMA GEMM, streaming TMA epilogue; 51 % of the iteration), the 6 forward GEMM shapes of one DiT block at M=%d" % M,
+    return {"bound": "tensor", "kernel": "gemm2_bf16_kernel<256|192, fast> (CTA-pair tcgen05/TMEM/TMA GEMM, streaming TMA epilogue; half of the iteration), the 6 forward GEMM shapes of one DiT block at M=%d" % M,
             "achieved": ach, "peak": peaks["burst"], "unit": "TFLOP/s", "frac": ach / peaks["burst"],
             "traffic": {"bytes_per_launch": 60.9e6, "shape": "8192x4608x1152 (FF1, bias + GELU-tanh)", "source": "ncu --set full, profiles/r01_ncu_full_v9_summary.txt"},
             "peak_source": peaks["source"] + ", burst figure (kernel timed alone)", "launches_timed": iters * len(shapes),

@@ -66,7 +66,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* q_full = bars;        // [2]
   uint64_t* q_empty = bars + 2;   // [2]
   uint64_t* s_full = bars + 4;    // [2]
-  uint64_t* p_full = bars + 6;
+  uint64_t* p_full = bars + 6;    // [2] by tile parity (bars + 6, bars + 7): see the MMA warp's wait
   uint64_t* pv_done = bars + 21;  // [2] by tile parity (see the softmax warps' waits)
   uint64_t* o_free = bars + 8;
   uint64_t* k_full = bars + 9;    // [3]
@@ -94,7 +94,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_empty[i], 1);
       mbar_init(&k_empty[i], 1);
     }
-    mbar_init(p_full, 256);
+    mbar_init(&p_full[0], 256);
+    mbar_init(&p_full[1], 256);
     mbar_init(&pv_done[0], 1);
     mbar_init(&pv_done[1], 1);
     mbar_init(o_free, 256);
@@ -178,7 +179,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (g + 1 < total_tiles) issue_qk(g + 1);
       const int it = g / n_kv, j = g - it * n_kv;
       const int st = g % KS;
-      mbar_wait(p_full, g & 1);
+      // S(g+1) is issued BEFORE this wait, so the softmax warps can finish tile g and tile g+1 (two arrivals) before this
+      // warp has observed the first: on one barrier the awaited parity would flip back and the wait never return
+      // (seen as a rare hang, adjacent CTAs at once).  One barrier per tile parity: tile g+2 needs S(g+2), which is
+      // only issued after this wait.
+      mbar_wait(&p_full[g & 1], (g >> 1) & 1);
       mbar_wait(&v_full[st], (uint32_t)(g / KS) & 1);
       if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);  // the previous item's epilogue has read O
       tc_fence_after();
@@ -305,7 +310,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st32(s_addr + wg * 32, sr);
         tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(p_full);
+        mbar_arrive(&p_full[buf]);
       }
       // combine the two halves' row sums (sL is only touched here: the barrier pair orders it against the last item)
       sL[wg * 128 + row] = l_run;
