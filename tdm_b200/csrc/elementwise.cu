@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(256) colreduce_kernel(ColRedArgs a) {
   if ((MODE == 1 || MODE == 3) && col_ok) gt = *reinterpret_cast<const float4*>(a.gate + (long)b * a.gate_stride + col);
   if (col_ok) {
     const int rend = min(row0 + a.rows_per_block, a.M);
+#pragma unroll 4  // independent rows: four rows of loads in flight per thread (the kernel is latency-, not bandwidth-bound)
     for (int r = row0 + threadIdx.y; r < rend; r += 8) {
       const long off = (long)r * a.ld + col;
       if (MODE == 0) {
