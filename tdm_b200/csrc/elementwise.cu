@@ -44,32 +44,51 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __res
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       }
   }
+  // modulation rows: loaded into registers now (in flight with the row loads), parked in shared memory only after the
+  // two reductions -- the CTA barrier then costs nothing, the loads have long landed
+  const int nq = D >> 2;
+  float4 m_sh[2], m_sc[2];
   if (one_sample) {
     const long mb0 = (long)(row0 / rows_per_sample) * mod_stride;
     const float4* sh = reinterpret_cast<const float4*>(shift + mb0);
     const float4* sc = reinterpret_cast<const float4*>(scale + mb0);
-    const int nq = D >> 2;
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-      ln_mod[i] = sh[i];
-      const float4 b = sc[i];
-      ln_mod[nq + i] = make_float4(1.f + b.x, 1.f + b.y, 1.f + b.z, 1.f + b.w);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < nq) {
+        m_sh[k] = sh[i];
+        m_sc[k] = sc[i];
+      }
+    }
+  }
+  float mean = 0.f, rstd = 0.f;
+  if (row < M) {
+    mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i)
+      if (i < nv) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+    rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+  if (one_sample) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int i = threadIdx.x + k * 256;
+      if (i < nq) {
+        ln_mod[i] = m_sh[k];
+        ln_mod[nq + i] = make_float4(1.f + m_sc[k].x, 1.f + m_sc[k].y, 1.f + m_sc[k].z, 1.f + m_sc[k].w);
+      }
     }
     __syncthreads();
   }
   if (row >= M) return;
-  const float mean = warp_sum(s) / (float)D;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
-    if (i < nv) {
-      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-      q += (a * a + b * b) + (c * c + d * d);
-    }
-  const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
   uint2* o = reinterpret_cast<uint2*>(out + (long)row * D);
   if (one_sample) {
     const int nq = D >> 2;
