@@ -157,7 +157,7 @@ class TdmTrainer:
 
     def __init__(self, student, fake, teacher, scheduler, uncond_ctx, uncond_mask, *, cfg=4.5, total_steps=900,
                  use_huber=True, use_separate=True, lowp=torch.bfloat16, lr=2e-5, lr_fake=2e-5, max_grad_norm=1.0,
-                 weight_decay=1e-2, grad_sync=None):
+                 weight_decay=1e-2, grad_sync=None, overlap_streams=None):
         self.student, self.fake, self.teacher = student, fake, teacher
         self.scheduler = scheduler
         self.cfg, self.total_steps, self.use_huber, self.use_separate = cfg, total_steps, use_huber, use_separate
@@ -174,6 +174,14 @@ class TdmTrainer:
         self.grad_sync = grad_sync
         self.world = grad_sync.world_size if grad_sync is not None else 1
         self.last = {}
+        # Two independent chains follow the trajectory: (fake-score forward -> its backward) and (teacher forward ->
+        # student forward).  On two streams the second chain's kernels fill the first chain's wave tails and the SMs its
+        # small LoRA-sized launches leave idle; they join at the loss.  Results are unchanged (same kernels, same order
+        # per tensor).  TDM_B200_OVERLAP=0 runs everything on one stream.
+        import os as _os
+        if overlap_streams is None:
+            overlap_streams = _os.environ.get("TDM_B200_OVERLAP", "1") != "0"
+        self._side = torch.cuda.Stream(device=dev) if overlap_streams else None
 
     # -- pieces -------------------------------------------------------------------------------------
     def _trajectory(self, noise, ctx, mask):
@@ -204,35 +212,51 @@ class TdmTrainer:
         latents_fake = pr.select_and_add_noise(rev_states[:4], k, noise_fake, t1, t_fake)
         x0_sel = ops.select_states(imgs_list[::-1], k)                      # the clean estimate behind that state
         x_in = ops.select_states(rev_states[1:5], k, out_dtype=self.lowp)   # the state the producing step started from
-        # ---- fake-score model: forward (saved) ----
+        side = self._side
+        main = torch.cuda.current_stream()
+        gs = self.grad_sync
+        from ._lib import check, ptr, stream_handle, lib, dtype_enum
+        if side is not None:
+            side.wait_stream(main)  # latents_fake, x_in, ctx are ready; the teacher / student were last used on `main`
+        # ---- side chain, part 1: frozen teacher (cond + uncond, x0 space; main.py:507-510, D4 mapping), then the
+        #      student forward with activations kept (its inputs do not depend on the loss) ----
+        with torch.cuda.stream(side if side is not None else main):
+            with torch.no_grad():
+                _, _, sd_latents, sd_latents_uncond = pr.predict(T, latents_fake, t_fake, ctx, mask, cfg=self.cfg, steps=1,
+                                                                 return_double=True, return_uncond=True)
+            out_s, saved_s = S._forward_impl(x_in, t_in, ctx, mask, True)
+        # ---- main chain: fake-score model forward (saved) ----
         out_fake, saved_f = Fk._forward_impl(latents_fake, t_fake, ctx, mask, True)
         _, x0_fake, _ = ops.solver_step(out_fake, latents_fake, t_fake, self.alpha_schedule, self.sigma_schedule,
                                         self.scheduler.config.prediction_type)   # main.py:484-490
         # effective noise of latents_fake w.r.t. x0_sel: (x - alpha x0) / sigma == predicted_origin with the tables swapped
         _, eps_target, _ = ops.solver_step(x0_sel, latents_fake, t_fake, self.sigma_schedule, self.alpha_schedule, "epsilon")
         loss_fake, g_fake = ops.mse_loss(out_fake, eps_target)
-        # ---- frozen teacher: cond + uncond, x0 space (main.py:507-510, D4 mapping) ----
-        with torch.no_grad():
-            _, _, sd_latents, sd_latents_uncond = pr.predict(T, latents_fake, t_fake, ctx, mask, cfg=self.cfg, steps=1,
-                                                             return_double=True, return_uncond=True)
-        # ---- score-difference loss (main.py:514-529) on the fake-vs-teacher x0 estimates; its closed-form
-        #      gradient lands on the student's x0 prediction of the step that produced the state ----
-        loss, g_x0 = ops.tdm_loss(x0_fake, sd_latents, sd_latents_uncond, self.cfg, self.use_huber)
-        # ---- student: forward with activations kept, backward through the solver step ----
-        out_s, saved_s = S._forward_impl(x_in, t_in, ctx, mask, True)
-        d_out_s = torch.empty_like(out_s)
-        from ._lib import check, ptr, stream_handle, lib, dtype_enum
-        check(lib().tdm_solver_step_bwd(0, ptr(g_x0), 1.0, 0, ptr(t_in), ptr(self.alpha_schedule),
-                                        ptr(self.sigma_schedule), dtype_enum(self.alpha_schedule),
-                                        self.alpha_schedule.numel(), ptr(d_out_s), 0, B, noise.shape[1], out_s.shape[1],
-                                        noise[0, 0].numel(), stream_handle()))
-        gs = self.grad_sync
-        S.backward_impl(saved_s, d_out_s, gs.hook(S) if gs is not None else None)
-        if gs is not None:
-            gs.finish(S)
+        x0_ready = torch.cuda.Event()
+        x0_ready.record(main)
+        # ---- side chain, part 2: score-difference loss (main.py:514-529) on the fake-vs-teacher x0 estimates; its
+        #      closed-form gradient lands on the student's x0 prediction of the step that produced the state; student
+        #      backward through the solver step ----
+        with torch.cuda.stream(side if side is not None else main):
+            if side is not None:
+                side.wait_event(x0_ready)
+            loss, g_x0 = ops.tdm_loss(x0_fake, sd_latents, sd_latents_uncond, self.cfg, self.use_huber)
+            d_out_s = torch.empty_like(out_s)
+            check(lib().tdm_solver_step_bwd(0, ptr(g_x0), 1.0, 0, ptr(t_in), ptr(self.alpha_schedule),
+                                            ptr(self.sigma_schedule), dtype_enum(self.alpha_schedule),
+                                            self.alpha_schedule.numel(), ptr(d_out_s), 0, B, noise.shape[1], out_s.shape[1],
+                                            noise[0, 0].numel(), stream_handle()))
+            # data parallel: every rank issues its bucketed all-reduces in the same host order (student buckets, then
+            # fake-score buckets); each one waits for the stream it was issued from
+            S.backward_impl(saved_s, d_out_s, gs.hook(S) if gs is not None else None)
+            if gs is not None:
+                gs.finish(S)
         Fk.backward_impl(saved_f, g_fake, gs.hook(Fk) if gs is not None else None)
         if gs is not None:
             gs.finish(Fk)
+        if side is not None:
+            main.wait_stream(side)
+        if gs is not None:
             gs.wait()
         inv = 1.0 / self.world
         self.opt_student.step(inv)
