@@ -1,12 +1,17 @@
 // tcgen05 / TMEM / TMA GEMM for sm_100a with a fused epilogue (see include/tdm_b200.h: TdmGemm).
 //
-// One persistent CTA per SM, 256 threads, warp-specialised:
-//   warp 0   : TMA producer  (one lane) -- fills a ring of {A 128x64, B BNx64} bf16 stages (SW128)
-//   warp 1   : MMA issuer    (one lane) -- tcgen05.mma 128xBNx16 into one of two TMEM accumulators
-//   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      -- tcgen05.ld (thread == accumulator row) -> fused math -> global
+// One persistent CTA per SM (gemm_bf16_kernel) or one CTA pair per SM pair (gemm2_bf16_kernel, cta_group::2: the
+// default for every large problem), 384 threads, warp-specialised:
+//   warp 0    : TMA producer  (one lane) -- fills a ring of {A 128x64, B BNx64 (or its half)} bf16 stages (SW128);
+//               the ring depth is chosen per launch from the shared memory the epilogue leaves free
+//   warp 1    : MMA issuer    (warp-convergent, tcgen05 ops under elect.sync) -- tcgen05.mma into one of two TMEM
+//               accumulators
+//   warp 2    : TMEM allocator
+//   warps 4-11: epilogue      -- tcgen05.ld (thread == accumulator row) -> fused math -> TMA stores
 // Three pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue), static tile loop.
-// Tails in M, N and K are handled by TMA out-of-bounds zero fill plus predicated stores.
+// Two epilogues: the streaming one (FAST kernels: every epilogue tensor moves by TMA, feature-specialised instances)
+// and the generic one (split-K reductions and the rare features); both produce bit-identical results.
+// Tails in M, N and K are handled by TMA out-of-bounds zero fill / clipping.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
