@@ -100,6 +100,11 @@ typedef struct TdmGemm {
   int32_t tile_n;  /* 0 = choose; else 64/128/192/256 */
   int32_t split_k; /* 0 = choose; >1 forces split-K (accumulate-only epilogues: res == out_f32, nothing else) */
   int32_t cta_pair; /* 0 = choose; 1 = one CTA per 128-row tile; 2 = CTA pair (cta_group::2) per 256-row tile */
+  /* Stacked problems that share one launch (single-CTA kernel, no second operand pair; seg_k needs K % 64 == 0):
+   *  seg_k  > 0 (with seg_n): output columns of segment s = n / seg_n contract over A columns / B rows
+   *            [s*seg_k, s*seg_k + K) and read B columns n - s*seg_n  (LoRA dt = dy_s B_s for stacked q/k/v)
+   *  seg_m  > 0: output rows of segment s = m / seg_m read B columns n + s*seg_nb          (LoRA dB_s = dy_s^T t_s) */
+  int32_t seg_k, seg_m, seg_nb;
   int32_t epilogue; /* 0 = choose; 1 = generic epilogue (direct loads / stores); 2 = streaming TMA epilogue with the
                        run-time tested code; 3 = streaming, feature-specialised instance when one exists (same results,
                        bit for bit: tests/test_gemm_gpu.py) */

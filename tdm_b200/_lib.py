@@ -74,7 +74,7 @@ class TdmGemm(C.Structure):
         ("res", vp), ("ld_res", i64), ("res_row_mod", i32),
         ("out_f32", vp), ("ld_out_f32", i64),
         ("out_bf16", vp), ("ld_out_bf16", i64),
-        ("tile_n", i32), ("split_k", i32), ("cta_pair", i32), ("epilogue", i32),
+        ("tile_n", i32), ("split_k", i32), ("cta_pair", i32), ("seg_k", i32), ("seg_m", i32), ("seg_nb", i32), ("epilogue", i32),
     ]
 
 

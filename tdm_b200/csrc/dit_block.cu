@@ -287,10 +287,26 @@ static int stacked_linear_bwd(const TdmDitShape* s, int nseg, const bf16* dy, in
   if (g_b) RUN(tdm_colsum_bf16(dy, n_out, tokens, n_out, g_b, st));
   const bool lora = r && la;
   if (lora) {
-    for (int j = 0; j < nseg; ++j) {
-      const bf16* lbj = reinterpret_cast<const bf16*>(lb) + (int64_t)j * seg_out * r;
-      RUN(lora_dt_db(s, dy + (int64_t)j * seg_out, n_out, seg_out, tokens, lbj, t + j * r, nseg * r, dt_buf + j * r,
-                     nseg * r, g_lb ? g_lb + (int64_t)j * seg_out * r : nullptr, st));
+    if (seg_out % 128 == 0) {
+      // every segment in ONE launch each: dt[:, s] = ls * dy[:, s] B_s (column segments shift the contraction window)
+      // and dB_s += dy[:, s]^T t[:, s] (row segments shift B's columns) -- the stacked [nseg * seg_out, r] matrices of
+      // lora_B and its gradient are contiguous
+      TdmGemm g = G(tokens, nseg * r, seg_out, dy, n_out, 0, lb, r, 1);
+      g.seg_n = r; g.seg_k = seg_out; g.tile_n = 64; g.cta_pair = 1;
+      g.alpha = s->lora_scale; g.out_bf16 = dt_buf; g.ld_out_bf16 = nseg * r;
+      RUN(tdm_gemm_bf16(&g, st));
+      if (g_lb) {
+        TdmGemm w = G(n_out, r, tokens, dy, n_out, 1, t, nseg * r, 1);
+        w.seg_m = seg_out; w.seg_nb = r; w.tile_n = 64; w.cta_pair = 1;
+        w.res = g_lb; w.ld_res = r; w.out_f32 = g_lb; w.ld_out_f32 = r;
+        RUN(tdm_gemm_bf16(&w, st));
+      }
+    } else {
+      for (int j = 0; j < nseg; ++j) {
+        const bf16* lbj = reinterpret_cast<const bf16*>(lb) + (int64_t)j * seg_out * r;
+        RUN(lora_dt_db(s, dy + (int64_t)j * seg_out, n_out, seg_out, tokens, lbj, t + j * r, nseg * r, dt_buf + j * r,
+                       nseg * r, g_lb ? g_lb + (int64_t)j * seg_out * r : nullptr, st));
+      }
     }
     if (g_la) RUN(wgrad(dt_buf, nseg * r, nseg * r, x, k_in, k_in, tokens, g_la, k_in, st));
   }

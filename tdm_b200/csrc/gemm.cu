@@ -27,6 +27,7 @@ struct GemmParams {
   int M, N, K, K2;
   int a_mn, b_mn;
   int seg_n, seg_k2;
+  int seg_k, seg_m, seg_nb;  // stacked problems in one launch (single-CTA kernel): see TdmGemm
   int num_m_tiles, num_n_tiles;
   int splits;        // split-K factor (>1 only in accumulate-only mode: partial sums are red.add'ed into out_f32)
   int stages;        // depth of the TMA<->MMA shared-memory ring (chosen on the host: what the epilogue leaves free)
@@ -635,6 +636,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m0 = (tile / p.num_n_tiles) * BM;
         const int n0 = (tile % p.num_n_tiles) * BN;
         const int seg = p.seg_n > 0 ? n0 / p.seg_n : 0;
+        // stacked problems: a column segment shifts the contraction window of both operands and restarts B's columns;
+        // a row segment shifts B's columns
+        const int k_off = p.seg_k > 0 ? seg * p.seg_k : 0;
+        const int bn0 = n0 - (p.seg_k > 0 ? seg * p.seg_n : 0) + (p.seg_m > 0 ? (m0 / p.seg_m) * p.seg_nb : 0);
         const int kb0 = (int)((long)sp * nk / p.splits), kb1 = (int)((long)(sp + 1) * nk / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -648,7 +653,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           const CUtensorMap* mA = &tmA;
           const CUtensorMap* mB = &tmB;
-          int ka = kb * BK, kbb = kb * BK;
+          int ka = kb * BK + k_off, kbb = kb * BK + k_off;
           if (kb >= nk1) {
             mA = &tmA2;
             mB = &tmB2;
@@ -662,10 +667,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_2d(sA + 8192, mA, &full_bar[stage], m0 + 64, ka);
           }
           if (!p.b_mn) {
-            tma_load_2d(sB, mB, &full_bar[stage], kbb, n0);
+            tma_load_2d(sB, mB, &full_bar[stage], kbb, bn0);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, mB, &full_bar[stage], n0 + 64 * j, kbb);
+            for (int j = 0; j < BN / 64; ++j) tma_load_2d(sB + j * 8192, mB, &full_bar[stage], bn0 + 64 * j, kbb);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -1046,8 +1051,13 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   constexpr int BOX_N = PAIR ? BN / 2 : BN;    // B rows one CTA stages per k-block
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc;
-  if ((rc = make_operand_map(&tmA, g->A, g->a_mn_major, g->M, g->K, g->lda, BM))) return rc;
-  if ((rc = make_operand_map(&tmB, g->B, g->b_mn_major, g->N, g->K, g->ldb, BOX_N))) return rc;
+  // stacked problems: the maps span every segment (A / B contraction extent nseg * seg_k, B columns per segment)
+  const long nseg_col = g->seg_k > 0 ? (g->N + g->seg_n - 1) / g->seg_n : 1;
+  const long nseg_row = g->seg_m > 0 ? (g->M + g->seg_m - 1) / g->seg_m : 1;
+  const long k_map = g->seg_k > 0 ? nseg_col * g->seg_k : g->K;
+  const long n_map = g->seg_k > 0 ? g->seg_n : (g->seg_m > 0 ? g->N + (nseg_row - 1) * g->seg_nb : g->N);
+  if ((rc = make_operand_map(&tmA, g->A, g->a_mn_major, g->M, k_map, g->lda, BM))) return rc;
+  if ((rc = make_operand_map(&tmB, g->B, g->b_mn_major, n_map, k_map, g->ldb, BOX_N))) return rc;
   if (g->K2 > 0) {
     const long a2_cols = g->seg_n > 0 ? (long)((g->N + g->seg_n - 1) / g->seg_n) * g->seg_k2 : g->K2;
     if ((rc = make_operand_map(&tmA2, g->A2, g->a_mn_major, g->M, a2_cols, g->lda2, BM))) return rc;
@@ -1074,6 +1084,7 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   p.M = g->M; p.N = g->N; p.K = g->K; p.K2 = g->K2 > 0 ? g->K2 : 0;
   p.a_mn = g->a_mn_major; p.b_mn = g->b_mn_major;
   p.seg_n = g->seg_n; p.seg_k2 = g->seg_k2;
+  p.seg_k = g->seg_k; p.seg_m = g->seg_m; p.seg_nb = g->seg_nb;
   p.num_m_tiles = (g->M + TILE_M - 1) / TILE_M;
   p.num_n_tiles = (g->N + BN - 1) / BN;
   p.alpha = g->alpha; p.act = g->act; p.bias = g->bias;
@@ -1221,7 +1232,14 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
   int bn = g->tile_n;
   int pair = g->cta_pair;  // 0 choose, 1 single CTA, 2 CTA pair
   static const int env_pair = getenv("TDM_B200_GEMM_PAIR") ? atoi(getenv("TDM_B200_GEMM_PAIR")) : 0;  // debugging aid
-  if (pair == 0 && env_pair == 1) pair = 1;
+  if (pair == 0 && (env_pair == 1 || g->seg_k > 0 || g->seg_m > 0)) pair = 1;
+  if (g->seg_k > 0 || g->seg_m > 0) {
+    TDM_REQUIRE(g->K2 <= 0, "tdm_gemm_bf16: stacked problems take no second operand pair");
+    TDM_REQUIRE(g->seg_k <= 0 || (g->seg_n > 0 && g->seg_k >= g->K && g->K % 64 == 0),
+                "tdm_gemm_bf16: seg_k needs seg_n > 0, seg_k >= K and K %% 64 == 0");
+    TDM_REQUIRE(g->seg_m <= 0 || (g->seg_m % 128 == 0 && g->seg_nb > 0), "tdm_gemm_bf16: seg_m must be a multiple of 128 with seg_nb > 0");
+    TDM_REQUIRE(g->cta_pair != 2, "tdm_gemm_bf16: stacked problems run on the single-CTA kernel");
+  }
   TDM_REQUIRE(g->epilogue >= 0 && g->epilogue <= 3, "tdm_gemm_bf16: epilogue must be 0 (choose), 1 (generic), 2 or 3 (streaming)");
   TDM_REQUIRE(pair >= 0 && pair <= 2, "tdm_gemm_bf16: cta_pair must be 0 (choose), 1 (single) or 2 (pair)");
   auto cost = [&](int b, bool pr) {

@@ -28,7 +28,7 @@ def _req(t, dtype, name):
 
 def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a2=None, b2=None, seg_n=0, seg_k2=0,
          alpha=1.0, bias=None, act=ACT_NONE, act_in=None, pre_out=None, pre_out_f32=None, gate=None,
-         rows_per_gate=1, res=None, res_row_mod=0, out_f32=None, out_bf16=None, tile_n=0, split_k=0, cta_pair=0, epilogue=0):
+         rows_per_gate=1, res=None, res_row_mod=0, out_f32=None, out_bf16=None, tile_n=0, split_k=0, cta_pair=0, epilogue=0, seg_k=0, seg_m=0, seg_nb=0):
     """C[M,N] = alpha*(A.B^T + A2.B2^T) with the fused epilogue of include/tdm_b200.h (TdmGemm).
 
     a: [M,K] (or [K,M] when a_mn_major); b: [N,K] (or [K,N] when b_mn_major); 2-D views with unit
@@ -76,6 +76,13 @@ def gemm(a, b, *, a_mn_major=False, b_mn_major=False, a2=None, b2=None, seg_n=0,
     g.split_k = split_k
     g.cta_pair = cta_pair
     g.epilogue = epilogue
+    if seg_k or seg_m:  # stacked problems: the tensors span every segment, the descriptor holds ONE problem's K / N
+        g.seg_n, g.seg_k, g.seg_m, g.seg_nb = int(seg_n), int(seg_k), int(seg_m), int(seg_nb)
+        if seg_k:
+            nseg = g.K // int(seg_k)
+            g.K, g.N = int(seg_k), nseg * int(seg_n)
+        if seg_m:
+            g.N = int(seg_nb)
     check(_lib.lib().tdm_gemm_bf16(C.byref(g), stream_handle()))
 
 

@@ -215,3 +215,32 @@ def test_streaming_epilogue_refuses_what_it_does_not_cover():
     acc = torch.zeros(256, 128, device="cuda")
     with pytest.raises(_lib.TdmError):
         ops.gemm(a, w, res=acc[:100], res_row_mod=100, out_f32=acc, epilogue=3)
+
+
+def test_gemm_stacked_segments():
+    """seg_k: column segments contract over their own window of A / B (LoRA dt for stacked q/k/v); seg_m: row segments read
+    their own B columns (LoRA dB).  One launch must equal the per-segment launches bit for bit."""
+    from tdm_b200 import ops
+    tokens, D, r, nseg = 384, 256, 64, 3
+    dy = _mk((tokens, nseg * D), seed=31)
+    lb = _mk((nseg * D, r), 0.1, seed=32)          # stacked lora_B: [nseg * D, r]
+    t = _mk((tokens, nseg * r), seed=33)
+    # dt[:, s] = 0.5 * dy[:, s] @ B_s
+    dt_one = torch.zeros(tokens, nseg * r, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, lb, b_mn_major=True, alpha=0.5, out_bf16=dt_one, seg_n=r, seg_k=D, tile_n=64, cta_pair=1)
+    dt_ref = torch.zeros_like(dt_one)
+    for s in range(nseg):
+        ops.gemm(dy[:, s * D:(s + 1) * D], lb[s * D:(s + 1) * D], b_mn_major=True, alpha=0.5, out_bf16=dt_ref[:, s * r:(s + 1) * r])
+    torch.cuda.synchronize()
+    assert torch.equal(dt_one, dt_ref)
+    _close(dt_one[:, r:2 * r], 0.5 * dy[:, D:2 * D].float() @ lb[D:2 * D].float(), 6e-3, "dt segment 1")
+    # dB_s += dy[:, s]^T t[:, s]
+    g_one = torch.ones(nseg * D, r, device="cuda")
+    ops.gemm(dy, t, a_mn_major=True, b_mn_major=True, res=g_one, out_f32=g_one, seg_m=D, seg_nb=r, tile_n=64, cta_pair=1, split_k=1)
+    g_ref = torch.ones(nseg * D, r, device="cuda")
+    for s in range(nseg):
+        ops.gemm(dy[:, s * D:(s + 1) * D], t[:, s * r:(s + 1) * r], a_mn_major=True, b_mn_major=True, res=g_ref[s * D:(s + 1) * D],
+                 out_f32=g_ref[s * D:(s + 1) * D], tile_n=64, cta_pair=1, split_k=1)
+    torch.cuda.synchronize()
+    assert torch.equal(g_one, g_ref)
+    _close(g_one[D:2 * D], 1.0 + dy[:, D:2 * D].float().t() @ t[:, r:2 * r].float(), 2e-4, "dB segment 1")
