@@ -157,7 +157,7 @@ class TdmTrainer:
 
     def __init__(self, student, fake, teacher, scheduler, uncond_ctx, uncond_mask, *, cfg=4.5, total_steps=900,
                  use_huber=True, use_separate=True, lowp=torch.bfloat16, lr=2e-5, lr_fake=2e-5, max_grad_norm=1.0,
-                 weight_decay=1e-2, grad_sync=None, overlap_streams=None):
+                 weight_decay=1e-2, grad_sync=None, overlap_streams=None, defer_fake_opt=False):
         self.student, self.fake, self.teacher = student, fake, teacher
         self.scheduler = scheduler
         self.cfg, self.total_steps, self.use_huber, self.use_separate = cfg, total_steps, use_huber, use_separate
@@ -182,6 +182,12 @@ class TdmTrainer:
         if overlap_streams is None:
             overlap_streams = _os.environ.get("TDM_B200_OVERLAP", "1") != "0"
         self._side = torch.cuda.Stream(device=dev) if overlap_streams else None
+        # Optional: the fake-score optimiser step (HBM-bound, ~2.4 ms) of iteration i runs on the side stream under the
+        # trajectory forwards of iteration i+1 (which only touch the student); the fake-score forward waits for it.
+        # Whoever reads the fake-score weights from outside calls sync() first.  Off by default; bench.py turns it on and
+        # closes its timed region with sync().
+        self.defer_fake_opt = bool(defer_fake_opt) and self._side is not None
+        self._fake_opt_evt = None
 
     # -- pieces -------------------------------------------------------------------------------------
     def _trajectory(self, noise, ctx, mask):
@@ -226,6 +232,7 @@ class TdmTrainer:
                                                                  return_double=True, return_uncond=True)
             out_s, saved_s = S._forward_impl(x_in, t_in, ctx, mask, True)
         # ---- main chain: fake-score model forward (saved) ----
+        self.sync()  # a deferred optimiser step of the previous iteration has to land first
         out_fake, saved_f = Fk._forward_impl(latents_fake, t_fake, ctx, mask, True)
         _, x0_fake, _ = ops.solver_step(out_fake, latents_fake, t_fake, self.alpha_schedule, self.sigma_schedule,
                                         self.scheduler.config.prediction_type)   # main.py:484-490
@@ -260,11 +267,25 @@ class TdmTrainer:
             gs.wait()
         inv = 1.0 / self.world
         self.opt_student.step(inv)
-        self.opt_fake.step(inv)
         self.opt_student.zero_grad()
-        self.opt_fake.zero_grad()
+        if self.defer_fake_opt:
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.opt_fake.step(inv)
+                self.opt_fake.zero_grad()
+                self._fake_opt_evt = torch.cuda.Event()
+                self._fake_opt_evt.record(side)
+        else:
+            self.opt_fake.step(inv)
+            self.opt_fake.zero_grad()
         self.last = {"loss": loss, "loss_fake": loss_fake, "ind_t": ind_t, "t_fake": t_fake, "t1": t1, "t_in": t_in}
         return {"loss": loss, "loss_fake": loss_fake}
+
+    def sync(self):
+        """Make the current stream wait for a deferred fake-score optimiser step (no-op otherwise)."""
+        if self._fake_opt_evt is not None:
+            torch.cuda.current_stream().wait_event(self._fake_opt_evt)
+            self._fake_opt_evt = None
 
     def step_from_host(self, noise_host, ctx_host, mask_host):
         """Public end-to-end entry: pinned HOST buffers in, host loss out (what bench.py's `e2e` times)."""

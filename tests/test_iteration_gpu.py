@@ -157,3 +157,33 @@ def test_sampling_4nfe_matches_oracle():
     got = sample_4nfe(ours.student, harness.make_scheduler(), noise.cuda(), ctx.cuda(), mask.cuda(), lowp=LOWP)
     assert got.dtype == torch.float32 and got.shape == ref.shape
     assert _rel(got, ref) < 3e-2
+
+
+def test_deferred_fake_optimizer_gives_the_same_iterations():
+    """TdmTrainer(defer_fake_opt=True) runs the fake-score optimiser step of iteration i on the side stream under the
+    trajectory of iteration i+1: losses and both models' weights after sync() must match the in-order run (same kernels,
+    same order per tensor; fp32 atomics in the backward reductions make two runs differ in the last bits only)."""
+    from tdm_b200 import harness
+    from tdm_b200.training import TdmTrainer
+    results = []
+    for defer in (False, True):
+        torch.manual_seed(7)
+        torch.cuda.manual_seed(7)
+        student, fake, teacher = harness.make_models("tiny", seed=0, device="cuda", lora_rank=64)
+        ctx, mask, uctx, umask = harness.synthetic_text(2, seed=5, Cc=student.Cc)
+        tr = TdmTrainer(student, fake, teacher, harness.make_scheduler(), uctx.cuda(), umask.cuda(), lr=1e-3, lr_fake=1e-3,
+                        defer_fake_opt=defer)
+        S = student.sample_size
+        losses = []
+        for i in range(4):
+            torch.manual_seed(100 + i)
+            noise = torch.randn(2, 4, S, S).to(torch.bfloat16).cuda()
+            out = tr.step(noise, ctx.cuda(), mask.cuda())
+            losses.append((out["loss"].item(), out["loss_fake"].item()))
+        tr.sync()
+        torch.cuda.synchronize()
+        results.append((losses, fake._flat.clone(), student._lflat.clone()))
+    for (l0, f0), (l1, f1) in zip(results[0][0], results[1][0]):
+        assert abs(l0 - l1) <= 1e-3 * abs(l0) + 1e-6 and abs(f0 - f1) <= 1e-3 * abs(f0) + 1e-6
+    assert _rel(results[1][1], results[0][1]) < 1e-4   # fake-score weights after four optimiser steps
+    assert _rel(results[1][2], results[0][2]) < 1e-3   # student LoRA weights
