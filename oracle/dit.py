@@ -142,6 +142,10 @@ class PatchEmbed(nn.Module):
 
 
 class Attention(nn.Module):
+    # bench.py's baselines may switch the softmax(QK^T)V evaluation to torch's fused SDPA (same function, no S
+    # materialised: the stand-in for the reference's xformers call, main.py:177-178); parity tests keep the explicit form
+    use_sdpa = False
+
     def __init__(self, d, heads):
         super().__init__()
         self.heads = heads
@@ -157,10 +161,14 @@ class Attention(nn.Module):
         q = self.to_q(x).view(B, N, h, D // h).transpose(1, 2)
         k = self.to_k(ctx).view(B, -1, h, D // h).transpose(1, 2)
         v = self.to_v(ctx).view(B, -1, h, D // h).transpose(1, 2)
-        s = torch.matmul(q, k.transpose(-1, -2)) * (D // h) ** -0.5
-        if bias is not None:
-            s = s + bias[:, None]  # [B,1,1,L] broadcast over heads and queries
-        o = torch.matmul(torch.softmax(s, dim=-1), v)
+        if self.use_sdpa:
+            m = None if bias is None else bias[:, None].to(q.dtype).expand(B, h, N, k.shape[2])
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=m, scale=(D // h) ** -0.5)
+        else:
+            s = torch.matmul(q, k.transpose(-1, -2)) * (D // h) ** -0.5
+            if bias is not None:
+                s = s + bias[:, None]  # [B,1,1,L] broadcast over heads and queries
+            o = torch.matmul(torch.softmax(s, dim=-1), v)
         o = o.transpose(1, 2).reshape(B, N, D)
         return self.to_out[0](o)
 

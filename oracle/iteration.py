@@ -107,7 +107,7 @@ class RepairedIteration:
         k, t1, t2, t_in = repaired_levels(ind_t, t_fake_draw, self.total_steps, self.use_separate)
         # per-sample select fused with predictor.add_noise: the kernel reads each state in its own dtype
         sel = torch.stack([self.predictor.add_noise(s, noise_fake, t1, t2) for s in states[:4]])
-        latents_fake = sel[k, torch.arange(B)]                                                      # main.py:479 (D2)
+        latents_fake = sel[k, torch.arange(B, device=k.device)]                                                      # main.py:479 (D2)
         x0_sel = _gather(imgs_list[::-1], k)
         x_in = _gather(states[1:5], k).to(self.lowp)
         pt = self.scheduler.config.prediction_type

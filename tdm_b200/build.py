@@ -24,24 +24,6 @@ NVCC_FLAGS = [
 ]
 
 
-def _nccl_paths():
-    """NCCL headers + the torch-bundled runtime library (system libnccl as a fallback)."""
-    inc, lib = None, None
-    try:
-        import nvidia.nccl as _n  # type: ignore
-
-        base = Path(list(_n.__path__)[0])
-        if (base / "include" / "nccl.h").exists():
-            inc = base / "include"
-        if (base / "lib" / "libnccl.so.2").exists():
-            lib = base / "lib"
-    except Exception:
-        pass
-    if inc is None and Path("/usr/include/nccl.h").exists():
-        inc = Path("/usr/include")
-    return inc, lib
-
-
 def sources():
     return sorted(CSRC.glob("*.cu"))
 
@@ -57,13 +39,11 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     nvcc = os.environ.get("NVCC", "nvcc")
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((ROOT.parent / "include").glob("*.h"))
-    inc, _ = _nccl_paths()
-    extra = ["-I", str(inc)] if inc else []
     jobs = []
     for src in sources():
         obj = OBJ / (src.stem + ".o")
         if force or _needs(obj, src, headers):
-            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
+            cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             jobs.append(cmd)
@@ -80,7 +60,8 @@ def build(verbose: bool = False, force: bool = False) -> Path:
             list(ex.map(run, jobs))
     objs = [str(OBJ / (s.stem + ".o")) for s in sources()]
     if jobs or not LIB.exists():
-        # libnccl is dlopen()ed at run time (dp.cu), libcuda through cudaGetDriverEntryPoint.
+        # libcuda's tensor-map encoder is resolved through cudaGetDriverEntryPoint at run time; the gradient exchange
+        # is torch.distributed (tdm_b200/dp.py), so the library links neither NCCL nor libcuda.
         cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

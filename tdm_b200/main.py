@@ -6,9 +6,10 @@ DESIGN.md section 2 lists them), running entirely on libtdm_b200.
                                                                             # script with this driver installed as src.main
 
 The reference's setup needs the network (T5, TAESD, the PixArt checkpoint, JourneyDB), so the offline
-harness provides random-init models and synthetic T5 embeddings (north_star); `--pretrained_provider module:function`
-lets a deployment plug real weights in.  Flags are the reference's (src/args.py); when /root/reference is importable
-its parser is used verbatim, otherwise the TDM-relevant subset below (unknown flags are accepted and ignored)."""
+harness provides random-init models and synthetic T5 embeddings (north_star); `Transformer2DModel._pretrained_provider`
+lets a deployment plug real weights in.  Flags are the reference's (src/args.py);
+its parser is used verbatim when TDM_REFERENCE_ROOT names a checkout, otherwise the TDM-relevant subset below (unknown
+flags are accepted and ignored)."""
 from __future__ import annotations
 
 import argparse
@@ -20,21 +21,37 @@ import time
 import torch
 
 
+DEFAULT_MAX_STEPS = 100  # the synthetic harness has no dataset length to derive num_train_epochs * steps from
+
+
+def _reference_parser():
+    """The reference's own `parse_args` (src/args.py imports without diffusers / accelerate), loaded by file path when a
+    checkout is named by TDM_REFERENCE_ROOT; None otherwise.  Nothing outside that variable is searched."""
+    root = os.environ.get("TDM_REFERENCE_ROOT")
+    if not root:
+        return None
+    path = os.path.join(root, "src", "args.py")
+    if not os.path.exists(path):
+        return None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("tdm_reference_args", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.parse_args
+
+
+IGNORED_FLAGS = ("gradient_accumulation_steps", "scale_lr", "num_train_epochs", "use_8bit_adam")
+
+
 def parse_args(argv=None):
-    try:  # the reference's own parser, unmodified (imports fine without diffusers / accelerate)
-        sys.path.insert(0, "/root/reference")
-        from src.args import parse_args as ref_parse  # type: ignore
+    ref_parse = _reference_parser()
+    if ref_parse is not None:
         old = sys.argv
         sys.argv = [old[0]] + list(argv if argv is not None else old[1:])
         try:
             return ref_parse()
         finally:
             sys.argv = old
-    except Exception:
-        pass
-    finally:
-        if sys.path and sys.path[0] == "/root/reference":
-            sys.path.pop(0)
     p = argparse.ArgumentParser(description="TDM distillation (B200-native)")
     p.add_argument("--pretrained_model_name_or_path", default="PixArt-alpha/PixArt-XL-2-512x512")
     p.add_argument("--output_dir", default="tdm-output")
@@ -70,11 +87,12 @@ def parse_args(argv=None):
     return args
 
 
-def lr_at(args, step):
+def lr_at(args, step, total=None):
     """diffusers.optimization.get_scheduler for the schedules the README uses (constant / constant_with_warmup /
     cosine_with_restarts with one cycle == cosine), evaluated on the host per step."""
     import math
-    name, warm, total = args.lr_scheduler, args.lr_warmup_steps, max(1, args.max_train_steps or 1)
+    name, warm = args.lr_scheduler, args.lr_warmup_steps
+    total = max(1, total if total is not None else (args.max_train_steps or DEFAULT_MAX_STEPS))
     if name == "constant":
         return args.learning_rate
     if step < warm:
@@ -100,6 +118,10 @@ def main(argv=None):
     dev = torch.device("cuda", local)
     if args.seed is not None:
         torch.manual_seed(args.seed)  # accelerate.utils.set_seed seeds every rank identically (main.py:117-118)
+    for flag in IGNORED_FLAGS:  # accepted for CLI compatibility, without effect here
+        v, d = getattr(args, flag, None), {"gradient_accumulation_steps": 1, "num_train_epochs": 100}.get(flag, False)
+        if v not in (None, d) and rank == 0:
+            print(f"tdm_b200.main: --{flag}={v} is accepted but has no effect in this driver", file=sys.stderr)
     lowp = torch.float16 if args.mixed_precision == "fp16" else torch.bfloat16
     cfg = harness.CONFIGS[config]
     S = cfg["sample_size"]
@@ -123,13 +145,21 @@ def main(argv=None):
         opt.betas, opt.eps = (args.adam_beta1, args.adam_beta2), args.adam_epsilon
     ema = EMAModel(student) if args.use_ema else None
     os.makedirs(args.output_dir, exist_ok=True)
-    global_step = ck.load_checkpoint(args.output_dir, args.resume_from_checkpoint, trainer) if args.resume_from_checkpoint else 0
-    max_steps = args.max_train_steps or 100
+    global_step = ck.load_checkpoint(args.output_dir, args.resume_from_checkpoint, trainer, ema) \
+        if args.resume_from_checkpoint else 0
+    max_steps = args.max_train_steps or DEFAULT_MAX_STEPS
     fixed_noise = draw_iteration_noise(4, (S, S), lowp, dev)  # main.py:544-547 (fixed validation noise)
+    vctx, vmask, _, _ = harness.synthetic_text(4, seed=(args.seed or 0) + 911, Cc=cfg["caption_channels"])  # 4 fixed prompts
+    vctx, vmask = vctx.to(dev).to(torch.bfloat16), vmask.to(dev)
+    # data stream: the model init above is identical on every rank; from here each rank draws its own noise / indices
+    # (accelerate's set_seed would leave all ranks on one stream, i.e. N copies of the same batch)
+    if world > 1 and not args.resume_from_checkpoint:
+        torch.manual_seed((args.seed or 0) + 1000 + rank)
+        torch.cuda.manual_seed((args.seed or 0) + 1000 + rank)
     log = open(os.path.join(args.output_dir, f"train_log_rank{rank}.jsonl"), "a")
     t0 = time.time()
     while global_step < max_steps:
-        lr = lr_at(args, global_step)
+        lr = lr_at(args, global_step, max_steps)
         trainer.opt_student.lr = trainer.opt_fake.lr = lr
         noise = draw_iteration_noise(B, (S, S), lowp, dev)                     # main.py:443
         out = trainer.step(noise, ctx, mask)
@@ -144,10 +174,10 @@ def main(argv=None):
             if rank == 0:
                 print(json.dumps(rec), flush=True)
         if rank == 0 and global_step % 50 == 0:                                  # main.py:542-549, training.py:107-112
-            lat4 = sample_4nfe(student, sched, fixed_noise, ctx[:4], mask[:4], lowp)
+            lat4 = sample_4nfe(student, sched, fixed_noise, vctx, vmask, lowp)
             torch.save(lat4.cpu(), os.path.join(args.output_dir, f"fixed_4step_{global_step}.pt"))
         if rank == 0 and global_step % args.checkpointing_steps == 0:            # main.py:563-587
-            ck.save_checkpoint(args.output_dir, global_step, trainer, args.checkpoints_total_limit)
+            ck.save_checkpoint(args.output_dir, global_step, trainer, args.checkpoints_total_limit, ema=ema)
     log.close()
     return 0
 

@@ -125,7 +125,12 @@ class Predictor:
                                                        self.sigma_schedule, 1.0, pred_type)
                         return score_pred_cfg, pred_latents, pred_latents_nocfg, pred_latents_uncond
                     return score_pred_cfg, pred_latents, pred_latents_nocfg
-                if steps > 1:  # with steps == 1 the re-noised sample is never used
+                # predictor.py:58.  With steps == 1 the re-noised sample is never used and is skipped.
+                # Deliberate deviation for steps > 1 under autograd: the reference detaches pred_latents only, so a
+                # gradient could reach the next step's INPUT through score_pred_cfg; the scheduler kernel is not
+                # differentiable and the hot path (main.py:507-512, steps=1) never takes that route, so both operands
+                # are detached here.  Values are identical.
+                if steps > 1:
                     noisy_samples = self.noise_scheduler.add_noise(pred_latents.detach(), score_pred_cfg.detach(),
                                                                    timesteps.long())
             else:

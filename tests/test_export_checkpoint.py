@@ -7,7 +7,11 @@ import types
 import pytest
 import torch
 
+from pathlib import Path
+
 from oracle import reference_import
+
+ROOT = Path(__file__).resolve().parents[1]
 
 
 class _FakeLoraModel:
@@ -140,3 +144,71 @@ def test_driver_runs_with_the_reference_cli(tmp_path, monkeypatch):
     assert drv.main(argv[:3] + ["14"] + argv[4:] + ["--resume_from_checkpoint", "latest"]) == 0
     recs = [json.loads(l) for l in open(os.path.join(out, "train_log_rank0.jsonl"))]
     assert recs[-1]["step"] == 14
+
+
+@pytest.mark.gpu
+def test_checkpoint_with_deferred_optimizer_and_ema(tmp_path):
+    """with defer_fake_opt the fake-score AdamW of the last step may still be running on the side stream when
+    a checkpoint is taken; trainer_state()/load_trainer_state() join it.  The EMA shadow and its step counter travel
+    with the checkpoint; the file holds plain tensors / ints only (weights_only=True)."""
+    from tdm_b200 import checkpoint as ck, harness
+    from tdm_b200.training import EMAModel, TdmTrainer, draw_iteration_noise
+    torch.manual_seed(0)
+    student, fake, teacher = harness.make_models("tiny", seed=0, device="cuda", lora_rank=64)
+    ctx, mask, uctx, umask = harness.synthetic_text(2, L=24, seed=0)
+    tr = TdmTrainer(student, fake, teacher, harness.make_scheduler(), uctx.cuda(), umask.cuda(), lr=1e-3, lr_fake=1e-3,
+                    defer_fake_opt=True)
+    assert tr.defer_fake_opt
+    ema = EMAModel(student)
+    for _ in range(3):
+        tr.step(draw_iteration_noise(2, (32, 32), torch.bfloat16, "cuda"), ctx.cuda(), mask.cuda())
+        ema.step(student.parameters())
+    st = ck.trainer_state(tr, ema)           # no explicit sync by the caller
+    torch.cuda.synchronize()
+    assert torch.equal(st["fake"], fake._flat.cpu())                       # not a torn copy of a step in flight
+    assert torch.equal(st["opt_fake.m0"], tr.opt_fake.state[0][0].cpu())
+    path = ck.save_checkpoint(str(tmp_path), 3, tr, ema=ema)
+    raw = torch.load(os.path.join(path, "trainer_state.pt"), weights_only=True)
+    assert raw["ema.step"] == 3 and raw["opt_fake.t"] == 3
+    shadow = [s.clone() for s in ema.shadow]
+    tr.step(draw_iteration_noise(2, (32, 32), torch.bfloat16, "cuda"), ctx.cuda(), mask.cuda())
+    ema.step(student.parameters())
+    assert ck.load_checkpoint(str(tmp_path), "latest", tr, ema) == 3
+    assert ema.optimization_step == 3 and all(torch.equal(a, b) for a, b in zip(shadow, ema.shadow))
+    assert torch.equal(fake._flat.cpu(), st["fake"]) and tr.opt_fake.t == 3
+    # main.py:389-393: a named checkpoint that is not there -> message, fresh run
+    assert ck.load_checkpoint(str(tmp_path), "checkpoint-77", tr, ema) == 0
+    assert ck.load_checkpoint(str(tmp_path / "nowhere"), "latest", tr, ema) == 0
+
+
+@pytest.mark.gpu
+def test_run_demo_executes_the_reference_entry_script(tmp_path, monkeypatch):
+    """`python -m tdm_b200.main --run_demo train_tdm_demo.py <flags>`: the reference's entry script (train_tdm_demo.py:
+    21-24, `from src.main import main` + `main()` under the __main__ guard) runs unchanged with this driver installed as
+    src.main.  The script body is restated here (the reference tree does not travel to the GPU box)."""
+    import json
+    import subprocess
+    script = tmp_path / "train_tdm_demo.py"
+    script.write_text('"""entry point"""\n\nfrom src.main import main\n\nif __name__ == "__main__":\n    main()\n')
+    out = str(tmp_path / "demo")
+    env = dict(os.environ, TDM_B200_CONFIG="tiny", PYTHONPATH=str(ROOT))
+    env.pop("TDM_REFERENCE_ROOT", None)
+    r = subprocess.run([sys.executable, "-m", "tdm_b200.main", "--run_demo", str(script), "--train_batch_size", "2",
+                        "--max_train_steps", "10", "--use_huber", "--use_separate", "--cfg", "4.5", "--output_dir", out,
+                        "--seed", "1", "--dataset_name", "synthetic", "--mixed_precision", "bf16",
+                        "--lr_scheduler", "cosine", "--lr_warmup_steps", "2", "--gradient_accumulation_steps", "2"],
+                       env=env, capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "--gradient_accumulation_steps=2 is accepted but has no effect" in r.stderr
+    recs = [json.loads(l) for l in open(os.path.join(out, "train_log_rank0.jsonl"))]
+    assert recs[-1]["step"] == 10 and recs[-1]["lr"] > 0  # cosine over the resolved 10 steps, not collapsed to 0
+
+
+def test_lr_schedule_uses_the_resolved_step_count():
+    from tdm_b200 import main as drv
+    a = drv.parse_args(["--dataset_name", "x", "--lr_scheduler", "cosine", "--lr_warmup_steps", "10", "--learning_rate", "1e-4"])
+    assert a.max_train_steps is None
+    vals = [drv.lr_at(a, s, drv.DEFAULT_MAX_STEPS) for s in (0, 5, 10, 55, 99)]
+    assert vals[0] == 0.0 and abs(vals[1] - 5e-5) < 1e-12 and abs(vals[2] - 1e-4) < 1e-12
+    assert abs(vals[3] - 5e-5) < 1e-9 and 0 < vals[4] < 1e-6
+    assert drv.lr_at(a, 50) == drv.lr_at(a, 50, drv.DEFAULT_MAX_STEPS)   # same default inside and outside the loop
