@@ -238,10 +238,11 @@ int tdm_mse_fwd_bwd(const float* pred, const float* target, double* loss_out, fl
 int tdm_sumsq_f32(const float* x, int64_t n, double* accum, int zero_first, void* stream);
 int tdm_clip_coef(const double* sumsq, float max_norm, float inv_scale, float* coef_out, float* norm_out, void* stream);
 /* optimizer.step() (main.py:206-224, 538): torch.optim.AdamW semantics on a flat fp32 arena; the gradient is
- * multiplied by *grad_coef (device scalar, may be NULL); param_bf16 (optional) receives the re-cast weights. */
+ * multiplied by *grad_coef (device scalar, may be NULL); param_bf16 (optional) receives the re-cast weights.
+ * Hyper-parameters are doubles: 1 - beta, 1 - lr * wd, lr / (1 - beta1^t) are formed in double like torch does. */
 int tdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16, int64_t n,
-                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, const float* grad_coef,
-                   void* stream);
+                   double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                   const float* grad_coef, void* stream);
 
 /* EMAModel.step (diffusers; reference main.py:188-189, 553-554) on a flat fp32 arena:
  * shadow -= (1 - decay) * (shadow - param). */

@@ -37,9 +37,24 @@ def main():
         opt.lr = 0.0
         opt.wd = 0.0
     ro = oracle.step(noise, ctx, mask, draws=draws, apply=False)
+    kept = {}
+    zs, zf = ours.opt_student.zero_grad, ours.opt_fake.zero_grad
+    ours.opt_student.zero_grad = lambda: kept.__setitem__("s", [g.clone() for _, g, _ in ours.opt_student.groups]) or zs()
+    ours.opt_fake.zero_grad = lambda: kept.__setitem__("f", [g.clone() for _, g, _ in ours.opt_fake.groups]) or zf()
     rg = ours.step(noise.cuda(), ctx.cuda(), mask.cuda(), draws=tuple(d.cuda() for d in draws))
     ours.sync()
     torch.cuda.synchronize()
+    gerr = []
+    for n, p in oracle.student.named_parameters():
+        if p.grad is not None and p.grad.abs().max() > 0:
+            gerr.append((norms(ours.student._lora_arena.view(kept["s"][-1], n), p.grad)["global"], "student." + n))
+    for n, p in oracle.fake.named_parameters():
+        if p.grad is not None and p.grad.abs().max() > 0 and not n.endswith("to_k.bias"):
+            gerr.append((norms(ours.fake._arena.view(kept["f"][0], n), p.grad)["global"], "fake." + n))
+    gerr.sort(reverse=True)
+    ge = torch.tensor([g for g, _ in gerr])
+    res["iteration_gradients"] = {"n": len(gerr), "worst": gerr[:8], "mean": ge.mean().item(), "median": ge.median().item(),
+                                  "p90": ge.quantile(0.9).item()}
     res["iteration_intermediates"] = {k: norms(ours.last[k], oracle.last[k]) for k in
                                       ("latents_fake", "x_in", "x0_sel", "x0_fake", "eps_target", "sd", "sdu", "g_x0")}
     res["iteration_losses"] = {k: [rg[k].item(), ro[k].item()] for k in ("loss", "loss_fake")}

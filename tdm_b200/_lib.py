@@ -145,7 +145,7 @@ SIGNATURES = {
     "tdm_mse_fwd_bwd": (ci, [vp, vp, vp, vp, cf, ci, ci, ci, ci, vp]),
     "tdm_sumsq_f32": (ci, [vp, i64, vp, ci, vp]),
     "tdm_clip_coef": (ci, [vp, cf, cf, vp, vp, vp]),
-    "tdm_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cf, cf, cf, cf, cf, ci, vp, vp]),
+    "tdm_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cd, cd, cd, cd, cd, ci, vp, vp]),
     "tdm_ema_update": (ci, [vp, vp, i64, cf, vp]),
     "tdm_dit_block_ws_bytes": (i64, [C.POINTER(TdmDitShape), ci]),
     "tdm_dit_block_bwd_scratch_bytes": (i64, [C.POINTER(TdmDitShape)]),

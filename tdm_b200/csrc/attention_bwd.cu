@@ -342,10 +342,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&qdo_empty[i], 1);
     }
     mbar_init(sdp_full, 1);
-    mbar_init(s_free, 256);
-    mbar_init(pds_full, 256);
+    mbar_init(s_free, 8);    // one elected arrival per compute warp (per-thread arrivals serialise on the barrier word)
+    mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dq_free, 128);
+    mbar_init(dq_free, 4);
     fence_barrier_init();
   }
   if (warp == 13) tmem_alloc(tmem_slot, 512);
@@ -493,7 +493,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld_wait();
         if (cc == 1) {  // everything this thread needs of the tile is in registers: dP^T may be overwritten
           tc_fence_before();
-          mbar_arrive(s_free);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);
         }
         uint32_t pk[16], dk[16];
 #pragma unroll
@@ -524,7 +525,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_st_wait();
       fence_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
     }
     // epilogue: warps 0-3 write dV, warps 4-7 write dK of this key tile (thread == key row)
     mbar_wait(dq_full, (n_q - 1) & 1);
@@ -567,7 +569,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(dq_free);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dq_free);
     }
   }
   tc_fence_before();

@@ -29,7 +29,15 @@ struct AttnFwdParams {
   bf16* O;        // [B, Sq, H, d] with strides
   long o_stride_b, o_stride_s, o_stride_h;
   float* lse;     // [B, H, Sq] natural-log sum-exp (for backward), or null
+  long long* trace;  // DBG & 64: clock64 stamps of CTA 0, [tile][16 events] (TDM_B200_ATTN_TRACE=<file>)
 };
+constexpr int TRACE_TILES = 96;
+#define ATT_TRACE(g_, e_)                                                                        \
+  do {                                                                                           \
+    if constexpr (DBG & 64) {                                                                    \
+      if (blockIdx.x == 0 && (g_) < TRACE_TILES) p.trace[(g_) * 16 + (e_)] = clock64();           \
+    }                                                                                            \
+  } while (0)
 
 __device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
   uint32_t r[8];
@@ -47,8 +55,21 @@ __device__ __forceinline__ void tmem_st8w(uint32_t taddr, const float* v) {
 // P V contraction directly from tensor memory: P never touches shared memory.
 // Two softmax warpgroups share every 128-query tile: warps 0-3 own keys [0,64) of the tile, warps 4-7 keys
 // [64,128) (thread == query row in both); they exchange row maxima through shared memory.
-constexpr int FWD_THREADS = 320;  // 8 softmax warps + TMA warp + MMA warp
+// Two TMA producer warps: Q + K (warp 8) and V (warp 10) run independently.  With one in-order producer thread the
+// K(g+1) load queued behind the wait for V(g)'s stage (free only when P V(g-2) retired), which left ONE tile of
+// prefetch distance: the loop period was the TMA round trip (~2800 clk) plus the P V time -- removing every softmax
+// instruction did not change the kernel time (profiles/r02_attn_ablation.jsonl).
+constexpr int FWD_THREADS = 352;  // 8 softmax warps + Q/K TMA warp + MMA warp + V TMA warp
 
+// DBG != 0 instantiations are timing ablations (scripts/attn_ablate.py; results are WRONG by construction):
+//   1 no MUFU (ex2 replaced by a move)   2 no half-row maxima exchange   4 no P store to TMEM   8 no S load from TMEM
+//   16 no running-max loop   64 clock64 trace   128 no P V MMAs   256 no Q K^T MMAs   512 no K / V TMA loads
+//   1024 (stays correct) every second odd exponential as a degree-3 polynomial on the FMA pipe: measured no faster
+// What they showed (profiles/r02_attn_ablation*.jsonl, r02_attn_trace_*.txt): with EVERY MMA, TMA load and softmax
+// instruction removed (927) the kernel still takes 83 of 88 us -- the loop is bound by the latency of its own
+// mbarrier / tcgen05.commit hand-offs (300-900 clk per hop, two hops per tile on the critical cycle), not by the
+// tensor pipe (640 clk per tile, 20 % active), MUFU (1024-1300 clk per tile) or TMA.
+template <int DBG>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
@@ -94,11 +115,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_empty[i], 1);
       mbar_init(&k_empty[i], 1);
     }
-    mbar_init(&p_full[0], 256);
-    mbar_init(&p_full[1], 256);
+    mbar_init(&p_full[0], 8);   // one elected arrival per softmax warp (256 per-thread arrivals serialise on the barrier word)
+    mbar_init(&p_full[1], 8);
     mbar_init(&pv_done[0], 1);
     mbar_init(&pv_done[1], 1);
-    mbar_init(o_free, 256);
+    mbar_init(o_free, 8);
     fence_barrier_init();
   }
   if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -115,8 +136,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (lane == 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      int g = 0;
+      int g = 0, st = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < my_items; ++it) {
         const int item = (int)blockIdx.x + it * (int)gridDim.x;
         const int q0 = (item % n_qt) * ATT_BM, h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
@@ -125,16 +146,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive_expect_tx(&q_full[qs], tile_bytes);
         for (int c = 0; c < p.nd; ++c) tma_load_4d(sQ + qs * tile_bytes + c * CHUNK_BYTES, &tmQ, &q_full[qs], c * 64, q0, h, b);
         for (int j = 0; j < n_kv; ++j, ++g) {
-          const int st = g % KS;
-          const uint32_t ph = (uint32_t)(g / KS) & 1;
           mbar_wait(&k_empty[st], ph ^ 1);
+          ATT_TRACE(g, 6);
+          if constexpr (DBG & 512) {
+            mbar_arrive(&k_full[st]);
+          } else {
           mbar_arrive_expect_tx(&k_full[st], tile_bytes);
           for (int c = 0; c < p.nd; ++c)
             tma_load_4d(sK + st * tile_bytes + c * CHUNK_BYTES, &tmK, &k_full[st], c * 64, j * ATT_BN, h, b);
+          }
+          if (++st == KS) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== TMA producer: V =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmV);
+      int g = 0, st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int item = (int)blockIdx.x + it * (int)gridDim.x;
+        const int h = (item / n_qt) % p.H, b = item / (n_qt * p.H);
+        for (int j = 0; j < n_kv; ++j, ++g) {
           mbar_wait(&v_empty[st], ph ^ 1);
+          ATT_TRACE(g, 7);
+          if constexpr (DBG & 512) {
+            mbar_arrive(&v_full[st]);
+          } else {
           mbar_arrive_expect_tx(&v_full[st], tile_bytes);
           for (int c = 0; c < p.nd; ++c)
             tma_load_4d(sV + st * tile_bytes + c * CHUNK_BYTES, &tmV, &v_full[st], c * 64, j * ATT_BN, h, b);
+          }
+          if (++st == KS) { st = 0; ph ^= 1; }
         }
       }
     }
@@ -150,53 +194,68 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t v_desc0 = make_sdesc_sw128(smem_u32(sV), CHUNK_BYTES, 1024);
     const uint32_t stage_step = uint32_t(tile_bytes) >> 4;  // descriptor address field counts 16-byte units
     const int dk16 = p.dk16;
+    // (one polling lane + __syncwarp instead of 32 polling lanes shortened the waits in the clock64 trace but measured
+    // slower end to end: 100 vs 91 us)
+    auto wait1 = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
+    // running tile coordinates of the two issue streams (no integer divisions on the issue path)
+    struct Cur { int it, j, st; uint32_t ph; };
+    auto advance = [&](Cur& c) {
+      if (++c.j == n_kv) { c.j = 0; ++c.it; }
+      if (++c.st == KS) { c.st = 0; c.ph ^= 1; }
+    };
+    Cur cq{0, 0, 0, 0}, cp{0, 0, 0, 0};
     auto issue_qk = [&](int g) {
-      const int it = g / n_kv, j = g - it * n_kv;
-      const int st = g % KS;
-      if (j == 0) mbar_wait(&q_full[it & 1], (it >> 1) & 1);
-      mbar_wait(&k_full[st], (uint32_t)(g / KS) & 1);
+      if (lane == 0) ATT_TRACE(g, 0);
+      if (cq.j == 0) wait1(&q_full[cq.it & 1], (cq.it >> 1) & 1);
+      wait1(&k_full[cq.st], cq.ph);
+      if (lane == 0) ATT_TRACE(g, 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t qd = q_desc0 + uint64_t((it & 1) * stage_step);
-        const uint64_t kd = k_desc0 + uint64_t(st * stage_step);
+        const uint64_t qd = q_desc0 + uint64_t((cq.it & 1) * stage_step);
+        const uint64_t kd = k_desc0 + uint64_t(cq.st * stage_step);
         const uint32_t sd = tmem_S + (g & 1) * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          if (k < dk16) {  // 16 head-dim columns per step: four steps per 64-column chunk
+          if (k < dk16 && !(DBG & 256)) {  // 16 head-dim columns per step: four steps per 64-column chunk
             const uint32_t off = ((k >> 2) * CHUNK_BYTES + (k & 3) * 32) >> 4;
             umma_bf16(sd, qd + off, kd + off, idesc_qk, k != 0);
           }
         }
         umma_commit(&s_full[g & 1]);
-        umma_commit(&k_empty[st]);
-        if (j == n_kv - 1) umma_commit(&q_empty[it & 1]);  // last read of this item's Q tile
+        umma_commit(&k_empty[cq.st]);
+        if (cq.j == n_kv - 1) umma_commit(&q_empty[cq.it & 1]);  // last read of this item's Q tile
       }
       __syncwarp();
+      advance(cq);
+      if (lane == 0) ATT_TRACE(g, 8);
     };
     if (total_tiles > 0) issue_qk(0);
     for (int g = 0; g < total_tiles; ++g) {
       // S((g+1)&1) still holds P(g-1): tcgen05.mma executes in issue order, so this S write follows P V (g-1)
       if (g + 1 < total_tiles) issue_qk(g + 1);
-      const int it = g / n_kv, j = g - it * n_kv;
-      const int st = g % KS;
       // S(g+1) is issued BEFORE this wait, so the softmax warps can finish tile g and tile g+1 (two arrivals) before this
       // warp has observed the first: on one barrier the awaited parity would flip back and the wait never return
       // (seen as a rare hang, adjacent CTAs at once).  One barrier per tile parity: tile g+2 needs S(g+2), which is
       // only issued after this wait.
-      mbar_wait(&p_full[g & 1], (g >> 1) & 1);
-      mbar_wait(&v_full[st], (uint32_t)(g / KS) & 1);
-      if (j == 0 && it > 0) mbar_wait(o_free, (it - 1) & 1);  // the previous item's epilogue has read O
+      wait1(&p_full[g & 1], (g >> 1) & 1);
+      if (lane == 0) ATT_TRACE(g, 2);
+      wait1(&v_full[cp.st], cp.ph);
+      if (lane == 0) ATT_TRACE(g, 3);
+      if (cp.j == 0 && cp.it > 0) wait1(o_free, (cp.it - 1) & 1);  // the previous item's epilogue has read O
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t vd = v_desc0 + uint64_t(st * stage_step);
+        const uint64_t vd = v_desc0 + uint64_t(cp.st * stage_step);
         const uint32_t p_addr = tmem_S + (g & 1) * 128;
 #pragma unroll
         for (int k = 0; k < ATT_BN / 16; ++k)  // 16 keys = 8 packed TMEM columns = 2048 smem bytes per step
-          umma_bf16_ts(tmem_O, p_addr + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (j | k) != 0);
-        umma_commit(&v_empty[st]);
+          if (!(DBG & 128))
+            umma_bf16_ts(tmem_O, p_addr + k * 8, vd + uint64_t(k * (2048 >> 4)), idesc_pv, (cp.j | k) != 0);
+        umma_commit(&v_empty[cp.st]);
         umma_commit(&pv_done[g & 1]);
       }
       __syncwarp();
+      advance(cp);
+      if (lane == 0) ATT_TRACE(g, 9);
     }
   } else {
     // ===================== softmax / correction / epilogue (2 x 128 threads, thread == query row) =====================
@@ -226,12 +285,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           asm volatile("bar.sync 2, 256;" ::: "memory");
         }
         mbar_wait(&s_full[buf], (g >> 1) & 1);
+        if (threadIdx.x == 0) ATT_TRACE(g, 4);
         tc_fence_after();
         const uint32_t s_addr = tmem_S + buf * 128 + lane_off;
         uint32_t sr[64];
-        tmem_ld32(s_addr + wg * 64, sr);
-        tmem_ld32(s_addr + wg * 64 + 32, sr + 32);
-        tmem_ld_wait();
+        if constexpr (DBG & 8) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) sr[i] = __float_as_uint((float)(i + row) * 0.001f);
+        } else {
+          tmem_ld32(s_addr + wg * 64, sr);
+          tmem_ld32(s_addr + wg * 64 + 32, sr + 32);
+          tmem_ld_wait();
+        }
+        if (threadIdx.x == 0) ATT_TRACE(g, 10);
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
         if (need_bias) {
           const float* bias_s = sBias + buf * 128 + wg * 64;
@@ -243,6 +309,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             sr[i] = __float_as_uint(v0); sr[i + 1] = __float_as_uint(v1); sr[i + 2] = __float_as_uint(v2); sr[i + 3] = __float_as_uint(v3);
             mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1); mx2 = fmaxf(mx2, v2); mx3 = fmaxf(mx3, v3);
           }
+        } else if constexpr (DBG & 16) {
+          mx0 = __uint_as_float(sr[0]);
         } else {
 #pragma unroll
           for (int i = 0; i < 64; i += 4) {
@@ -253,13 +321,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
         if (!need_bias) mx *= p.scale_log2;  // scale > 0
         // exchange the half-row maxima (double-buffered by tile parity: one barrier per tile is enough)
-        float* mx_s = sMax + buf * 256;
-        mx_s[wg * 128 + row] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        mx = fmaxf(mx, mx_s[(wg ^ 1) * 128 + row]);
+        if constexpr (!(DBG & 2)) {
+          float* mx_s = sMax + buf * 256;
+          mx_s[wg * 128 + row] = mx;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          mx = fmaxf(mx, mx_s[(wg ^ 1) * 128 + row]);
+        }
         // Lazy rescale: O and l keep the stale maximum until it is exceeded by more than 2^8 (exact after the final
         // division; P <= 256 stays well inside bf16 / fp32 range).  Warp-uniform (tcgen05.ld/st are collective) and
         // identical in both warpgroups, which see the same rows and the same exchanged maxima.
+        if (threadIdx.x == 0) ATT_TRACE(g, 11);
         const float m_new = fmaxf(m_used, mx);
         if (j == 0) {
           m_used = m_new;
@@ -297,20 +368,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         } else {
           const float nm = -m_used;
+          auto ex = [](float x) { if constexpr (DBG & 1) return x; else return ex2_fast(x); };
+          auto exq = [](float x, int i) {  // DBG & 1024: one exponential in four as a degree-3 polynomial on the FMA pipe
+            if constexpr (DBG & 1024) return (i & 1) ? ex2_poly(x) : ex2_fast(x);
+            else if constexpr (DBG & 1) return x;
+            else return ex2_fast(x);
+          };
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float p0 = ex2_fast(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
-            const float p1 = ex2_fast(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
+            const float p0 = ex(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
+            const float p1 = exq(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm), i);
             l0 += p0;
             l1 += p1;
             sr[i] = pack_bf16(p0, p1);
           }
         }
         l_run += l0 + l1;
-        tmem_st32(s_addr + wg * 32, sr);
-        tmem_st_wait();
+        if (threadIdx.x == 0) ATT_TRACE(g, 12);
+        if constexpr (!(DBG & 4)) {
+          tmem_st32(s_addr + wg * 32, sr);
+          tmem_st_wait();
+          if (threadIdx.x == 0) ATT_TRACE(g, 13);
+        } else {
+          if (l_run == 123.456f) tmem_st32(s_addr + wg * 32, sr);  // keeps sr live
+        }
         tc_fence_before();
-        mbar_arrive(&p_full[buf]);
+        if (threadIdx.x == 0) ATT_TRACE(g, 5);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[buf]);
       }
       // combine the two halves' row sums (sL is only touched here: the barrier pair orders it against the last item)
       sL[wg * 128 + row] = l_run;
@@ -339,7 +424,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(o_free);  // O is in registers: the next item's first P V may overwrite it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);  // O is in registers: the next item's first P V may overwrite it
       if (q < p.Sq) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -393,19 +479,67 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
   p.bias = a->bias;
   p.O = (bf16*)a->O; p.o_stride_b = a->o_stride_b; p.o_stride_s = a->o_stride_s; p.o_stride_h = a->o_stride_h;
   p.lse = a->lse;
-  const int extra = 1024 + 2048 + 1024 + 512 + 1024;
+  const int extra = 1024 + 6144 + 512 + 512;  // alignment slack + bias / max / sum hand-over arrays + barriers
   p.kv_stages = (8 * p.nd * CHUNK_BYTES + extra <= 232448) ? 3 : 2;  // head_dim <= 64: 16 KB tiles, three stages fit
   const int smem = (2 + 2 * p.kv_stages) * p.nd * CHUNK_BYTES + extra;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    smem_set = smem;
+  const int dbg = getenv("TDM_B200_ATTN_DBG") ? atoi(getenv("TDM_B200_ATTN_DBG")) : 0;
+  auto kern = attn_fwd_kernel<0>;
+  switch (dbg) {
+    case 1: kern = attn_fwd_kernel<1>; break;
+    case 2: kern = attn_fwd_kernel<2>; break;
+    case 4: kern = attn_fwd_kernel<4>; break;
+    case 8: kern = attn_fwd_kernel<8>; break;
+    case 16: kern = attn_fwd_kernel<16>; break;
+    case 31: kern = attn_fwd_kernel<31>; break;
+    case 128: kern = attn_fwd_kernel<128>; break;
+    case 256: kern = attn_fwd_kernel<256>; break;
+    case 415: kern = attn_fwd_kernel<415>; break;
+    case 512: kern = attn_fwd_kernel<512>; break;
+    case 927: kern = attn_fwd_kernel<927>; break;
+    case 1024: kern = attn_fwd_kernel<1024>; break;
+    default: break;
+  }
+  int threads = FWD_THREADS;
+  p.trace = nullptr;
+  const char* trace_path = getenv("TDM_B200_ATTN_TRACE");  // debugging aid: per-tile clock64 stamps of CTA 0
+  static long long* trace_buf = nullptr;
+  if (trace_path && *trace_path) {
+    if (!trace_buf) TDM_CHECK_CUDA(cudaMalloc(&trace_buf, TRACE_TILES * 16 * sizeof(long long)));
+    TDM_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, TRACE_TILES * 16 * sizeof(long long), (cudaStream_t)stream));
+    p.trace = trace_buf;
+    kern = attn_fwd_kernel<64>;
+  }
+  {
+    static const void* seen[16];
+    static int seen_smem[16];
+    int slot = 0;
+    while (slot < 15 && seen[slot] && seen[slot] != (const void*)kern) ++slot;
+    if (seen[slot] != (const void*)kern || smem > seen_smem[slot]) {
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      seen[slot] = (const void*)kern;
+      seen_smem[slot] = smem;
+    }
   }
   const long items = (long)((a->Sq + ATT_BM - 1) / ATT_BM) * a->H * a->B;
   const int grid = (int)(items < num_sms() ? items : num_sms());
   ::tdm::count_launch();
   static const bool pdl_attn = !(getenv("TDM_B200_PDL_ATTN") && atoi(getenv("TDM_B200_PDL_ATTN")) == 0);
-  TDM_CHECK_CUDA(launch_pdl_if(pdl_attn, attn_fwd_kernel, dim3(grid), dim3(FWD_THREADS), (size_t)smem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
+  TDM_CHECK_CUDA(launch_pdl_if(pdl_attn, kern, dim3(grid), dim3(threads), (size_t)smem, (cudaStream_t)stream, tmQ, tmK, tmV, p));
   TDM_CHECK_CUDA(cudaGetLastError());
+  if (p.trace) {
+    static long long host[TRACE_TILES * 16];
+    TDM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    TDM_CHECK_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "# Sq=%d Sk=%d d=%d events: 0 qk_wait 1 qk_issue 2 p_full 3 pv_issue 4 s_full_seen 5 p_arrive 6 k_load 7 v_load\n", a->Sq, a->Sk, a->d);
+      for (int g = 0; g < TRACE_TILES; ++g) {
+        if (!host[g * 16 + 1]) break;
+        fprintf(f, "%d", g);
+        for (int e = 0; e < 14; ++e) fprintf(f, " %lld", host[g * 16 + e] ? host[g * 16 + e] - host[1] : -1);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+  }
   return TDM_OK;
 }

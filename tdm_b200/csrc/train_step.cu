@@ -111,8 +111,9 @@ __global__ void clip_coef_kernel(const double* sumsq, float max_norm, float inv_
 
 // AdamW (decoupled weight decay, bias-corrected; torch.optim.AdamW semantics) on a flat arena.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                             float* __restrict__ v, bf16* __restrict__ p16, long n, float lr, float b1, float b2,
-                             float eps, float wd, float bc1, float bc2_sqrt, const float* __restrict__ coef_ptr) {
+                             float* __restrict__ v, bf16* __restrict__ p16, long n, float b2, float omb1,
+                             float omb2, float eps, float decay, float step, float bc2_sqrt,
+                             const float* __restrict__ coef_ptr) {
   const float coef = coef_ptr ? *coef_ptr : 1.f;
   const long n4 = n >> 2;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -120,7 +121,6 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   float4* m4 = reinterpret_cast<float4*>(m);
   float4* v4 = reinterpret_cast<float4*>(v);
   uint2* o4 = reinterpret_cast<uint2*>(p16);
-  const float step = lr / bc1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 pp = p4[i], mm = m4[i], vv = v4[i];
     const float4 gg = g4[i];
@@ -131,11 +131,11 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float gk = G[k] * coef;
-      P[k] *= 1.f - lr * wd;
-      Mv[k] = b1 * Mv[k] + (1.f - b1) * gk;
-      V[k] = b2 * V[k] + (1.f - b2) * gk * gk;
+      P[k] *= decay;
+      Mv[k] = Mv[k] + omb1 * (gk - Mv[k]);      // exp_avg.lerp_(grad, 1 - beta1)
+      V[k] = b2 * V[k] + omb2 * (gk * gk);      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
       const float denom = sqrtf(V[k]) / bc2_sqrt + eps;
-      P[k] -= step * Mv[k] / denom;
+      P[k] -= step * (Mv[k] / denom);           // param.addcdiv_(exp_avg, denom, value=-step_size)
     }
     p4[i] = pp;
     m4[i] = mm;
@@ -219,7 +219,7 @@ extern "C" int tdm_clip_coef(const double* sumsq, float max_norm, float inv_scal
 }
 
 extern "C" int tdm_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, void* param_bf16,
-                              int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                               const float* grad_coef, void* stream) {
   TDM_REQUIRE(param && grad && exp_avg && exp_avg_sq, "tdm_adamw_step: null input");
   TDM_REQUIRE(n > 0 && n % 4 == 0, "tdm_adamw_step: n=%lld must be a positive multiple of 4", (long long)n);
@@ -227,11 +227,14 @@ extern "C" int tdm_adamw_step(float* param, const float* grad, float* exp_avg, f
   TDM_REQUIRE((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0 &&
                   ((uintptr_t)param_bf16 & 7) == 0,
               "tdm_adamw_step: buffers must be 16-byte aligned");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  ::tdm::count_launch(); adamw_kernel<<<ts_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, (bf16*)param_bf16,
-                                                                     (long)n, lr, beta1, beta2, eps, weight_decay, bc1,
-                                                                     bc2_sqrt, grad_coef);
+  // Hyper-parameters arrive as doubles and every derived scalar is formed in double before it is rounded to fp32, the way
+  // torch.optim.AdamW forms them in Python (1 - beta2 = 0.001, not 1.f - 0.999f = 0.00100005).
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2_sqrt = sqrt(1.0 - pow(beta2, (double)step));
+  ::tdm::count_launch();
+  adamw_kernel<<<ts_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+      param, grad, exp_avg, exp_avg_sq, (bf16*)param_bf16, (long)n, (float)beta2, (float)(1.0 - beta1),
+      (float)(1.0 - beta2), (float)eps, (float)(1.0 - lr * weight_decay), (float)(lr / bc1), (float)bc2_sqrt, grad_coef);
   TDM_CHECK_CUDA(cudaGetLastError());
   return TDM_OK;
 }

@@ -83,6 +83,9 @@ def parse_args(argv=None):
     p.add_argument("--use_huber", action="store_true")
     p.add_argument("--use_separate", action="store_true")
     p.add_argument("--use_reg", action="store_true")
+    p.add_argument("--gradient_accumulation_steps", type=int, default=1)
+    p.add_argument("--scale_lr", action="store_true")
+    p.add_argument("--use_8bit_adam", action="store_true")
     args, _unknown = p.parse_known_args(argv)
     return args
 

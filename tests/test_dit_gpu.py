@@ -2,7 +2,9 @@
 weights and inputs: per-block outputs, model output, and every parameter gradient.
 
 Tolerance (north_star): per-block outputs within max relative error 2e-2 in bf16 against the fp32
-reference path, with the norm  max|a-b| / max|b|  over the tensor."""
+reference path, with the norm  max|a-b| / max|b|  over the tensor -- plus two norms that cannot hide small-magnitude
+entries behind one large one: per token row  max_row|a-b| / max_row|b| <= 1e-2, and mean|a-b| / mean|b| <= 5e-3.
+Measured on B200 (profiles/r02_parity_stats.json): 2.3e-3 global, 3.0e-3 per row, 1.4e-3 mean at the XL width."""
 import pytest
 import torch
 
@@ -14,6 +16,17 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
 def _rel(got, ref):
     return ((got.detach().float().cpu() - ref.detach().float().cpu()).abs().max() / (ref.detach().float().abs().max() + 1e-12)).item()
+
+
+def _rel_rows(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    got, ref = got.reshape(-1, got.shape[-1]), ref.reshape(-1, ref.shape[-1])
+    return ((got - ref).abs().max(dim=1).values / (ref.abs().max(dim=1).values + 1e-12)).max().item()
+
+
+def _rel_mean(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().mean() / (ref.abs().mean() + 1e-12)).item()
 
 
 def _inputs(cfg, B, L, seed=0):
@@ -72,6 +85,8 @@ def test_forward_per_block_and_output(cfg, B, L):
         got = saved.xs[i + 1].view(B, -1, cfg.inner_dim)
         e = _rel(got, ref.capture[f"block{i}"])
         assert e < 2e-2, f"block {i}: max rel err {e}"
+        assert _rel_rows(got, ref.capture[f"block{i}"]) < 1e-2, f"block {i}: per-row"
+        assert _rel_mean(got, ref.capture[f"block{i}"]) < 5e-3, f"block {i}: mean"
     assert out.shape == out_ref.shape == (B, 8, cfg.sample_size, cfg.sample_size)
     assert _rel(out, out_ref) < 2e-2
     # inference path (no saved activations) gives the same numbers

@@ -3,8 +3,12 @@
 
 * timestep / index selection: bit-exact (north_star);
 * every intermediate of one iteration within bf16 tolerance of the fp32 path;
-* losses within 1 % (mean over the run) across many optimiser steps on BASELINE.json configs[0]
-  (tiny DiT: 2 blocks, hidden 256, 32x32x4 latent, batch 2)."""
+* the TDM loss within 1 % on EVERY one of 100 iterations of BASELINE.json configs[0] (tiny DiT: 2 blocks, hidden 256,
+  32x32x4 latent, batch 2), optimiser steps applied on both sides.
+
+Measured on B200 (scripts/parity_stats.py -> profiles/r02_parity_stats.json): TDM loss deviation max 0.18 %, median
+0.003 %; intermediates 0.5-0.8 % of the largest entry (0.14-0.17 % of the mean magnitude); sign of the Huber gradient
+equal on 99.2 % of the entries."""
 import pytest
 import torch
 
@@ -21,6 +25,11 @@ LOWP = torch.bfloat16
 def _rel(got, ref):
     got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
     return ((got - ref).abs().max() / (ref.abs().max() + 1e-12)).item()
+
+
+def _mean_rel(got, ref):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    return ((got - ref).abs().mean() / (ref.abs().mean() + 1e-12)).item()
 
 
 def _build(seed=0, lora=True, lr=2e-5):
@@ -96,8 +105,24 @@ def test_one_iteration_intermediates_and_gradients():
     # integer selections: bit-exact
     for key in ("ind_t", "t_fake", "t1", "t_in"):
         assert torch.equal(ours.last[key].cpu(), oracle.last[key]), key
-    assert abs(rg["loss"].item() - ro["loss"].item()) <= 1e-2 * abs(ro["loss"].item())
-    assert abs(rg["loss_fake"].item() - ro["loss_fake"].item()) <= 2e-2 * abs(ro["loss_fake"].item())
+    assert abs(rg["loss"].item() - ro["loss"].item()) <= 2e-3 * abs(ro["loss"].item())
+    assert abs(rg["loss_fake"].item() - ro["loss_fake"].item()) <= 1e-2 * abs(ro["loss_fake"].item())
+    # every intermediate of the iteration: bf16 tensor-core DiT against the fp32 oracle.
+    # max|a-b| / max|b| <= 2e-2 (north_star's norm) AND mean|a-b| / mean|b| <= 5e-3 (no hiding behind one large entry)
+    for key in ("x_in", "x0_sel", "latents_fake", "x0_fake", "sd", "sdu"):
+        a, b = ours.last[key], oracle.last[key]
+        assert a.shape == b.shape, key
+        assert _rel(a, b) < 2e-2, (key, _rel(a, b))
+        assert _mean_rel(a, b) < 5e-3, (key, _mean_rel(a, b))
+    # eps_target = (x_t - alpha x0_sel) / sigma at t2 subtracts nearly equal quantities and divides by sigma_t2 (0.01 at
+    # t2 ~ 0): a 0.5 % difference of x0_sel is amplified by alpha/sigma (up to 67 for these draws), so only its mean
+    # error is meaningful
+    assert _mean_rel(ours.last["eps_target"], oracle.last["eps_target"]) < 5e-2
+    # closed-form Huber gradient (c = 1e-3): ~ sign(x0_fake - target) / (w_b n); the sign is noise where the difference
+    # is below bf16 resolution
+    g, gr = ours.last["g_x0"].cpu(), oracle.last["g_x0"].float()
+    assert (torch.sign(g) == torch.sign(gr)).float().mean().item() > 0.98
+    assert _mean_rel(g, gr) < 4e-2
     # student LoRA gradients and fake-score full gradients against autograd
     s_named = dict(ours.student.named_parameters())
     worst = []
@@ -115,7 +140,9 @@ def test_one_iteration_intermediates_and_gradients():
         worst.append((_rel(got, p.grad), "fake." + n))
     worst.sort(reverse=True)
     assert len(worst) > 40
-    assert worst[0][0] < 8e-2, worst[:6]
+    # bf16 gradient operands against fp32 autograd; measured on B200 (profiles/r02_parity_stats.json): worst 3.8e-2,
+    # mean 1.3e-2, median 0.9e-2 of the largest entry of each gradient tensor
+    assert worst[0][0] < 5e-2, worst[:6]
     assert sum(w for w, _ in worst) / len(worst) < 2e-2
     # the fused clip kernel saw the same global norm torch computes
     ref_norm = torch.nn.utils.clip_grad_norm_([p for p in oracle.fake.parameters() if p.grad is not None], 1e9)
@@ -123,8 +150,14 @@ def test_one_iteration_intermediates_and_gradients():
 
 
 def test_losses_track_the_oracle_over_many_iterations():
-    """BASELINE.json configs[0] / north_star: loss within 1 % over 100 iterations (here: mean over the run,
-    plus a per-iteration bound), identical seeds and draws on both sides."""
+    """BASELINE.json configs[0] / north_star: loss within 1 % over 100 iterations -- asserted on EVERY iteration for the
+    TDM loss (main.py:514-529), identical seeds and draws on both sides, optimiser steps applied on both sides.
+
+    The auxiliary fake-score MSE (repair D5; not a quantity of the reference) cannot meet 1 % per iteration in bf16 and
+    the test says so with numbers: loss_fake = mean((eps_fake - eps_target)^2) is the square of a RESIDUAL of two
+    O(1) quantities, so a bf16 forward error of ~0.5 % of eps becomes 2 * 0.005 * |eps| / |residual| ~ 1-2 % of the
+    loss, and eps_target itself divides by sigma_t2 (alpha/sigma up to 67 in these draws).  Measured on B200: median
+    0.37 %, 21 of 100 iterations above 1 %, max 4.1 % (iteration 48, t2 = 10); the mean over the run agrees to 0.4 %."""
     n_iter = 100
     oracle, ours, (ctx, mask) = _build(seed=3, lr=1e-4)
     lo, lg, fo, fg = [], [], [], []
@@ -136,12 +169,11 @@ def test_losses_track_the_oracle_over_many_iterations():
         fo.append(ro["loss_fake"].item()); fg.append(rg["loss_fake"].item())
     lo, lg, fo, fg = map(torch.tensor, (lo, lg, fo, fg))
     assert torch.isfinite(lg).all() and torch.isfinite(fg).all()
-    assert abs(lg.mean() - lo.mean()) <= 1e-2 * lo.mean().abs()
-    # the fake-score MSE has a heavy tail (t2 ~ t1 ~ 0 divides by sigma_t2 ~ 0.01): a few iterations dominate its
-    # mean, so the mean gets 2 % and the typical iteration (median) 1 %
-    assert abs(fg.mean() - fo.mean()) <= 2e-2 * fo.mean().abs()
-    assert ((lg - lo).abs() / lo.abs()).max() < 5e-2
-    assert ((fg - fo).abs() / fo.abs()).median() < 1e-2
+    assert ((lg - lo).abs() / lo.abs()).max() <= 1e-2          # north_star: every iteration within 1 %
+    assert abs(lg.mean() - lo.mean()) <= 2e-3 * lo.mean().abs()
+    dev_f = (fg - fo).abs() / fo.abs()
+    assert abs(fg.mean() - fo.mean()) <= 1e-2 * fo.mean().abs()
+    assert dev_f.median() < 1e-2 and dev_f.max() < 6e-2
 
 
 def test_sampling_4nfe_matches_oracle():
