@@ -482,6 +482,37 @@ def run_ours(args):
                     "unit": "final latents/s (4 NFE, timesteps 999/856/665/399), summed over GPUs", "batch_per_gpu": Bs,
                     "ms_per_batch": ms_s, "tflops_per_gpu": fl / (ms_s * 1e-3) / 1e12,
                     "frac_of_sustained_peak": fl / (ms_s * 1e-3) / 1e12 / peaks["sustained"]}
+        # ---- the step after sampling: TAESD decode to RGB, training.py:113-117 ----
+        try:
+            from tdm_b200.taesd import AutoencoderTiny, decode_to_images
+            vae = AutoencoderTiny(device=dev, seed=3)
+            for _ in range(2):
+                img = decode_to_images(vae, sample_4nfe(student, sched, snoise_d, sctx_d, smask_d, lowp))
+            barrier()
+            d0, d1, d2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            d0.record()
+            for _ in range(reps):
+                lat = sample_4nfe(student, sched, snoise_d, sctx_d, smask_d, lowp)
+            d1.record()
+            for _ in range(reps):
+                img = decode_to_images(vae, lat)
+            d2.record()
+            barrier()
+            td = torch.tensor([d0.elapsed_time(d1) / reps, d1.elapsed_time(d2) / reps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            ms_lat, ms_dec = td.tolist()
+            Hs = S * 8
+            conv_flops = 2.0 * 64 * 64 * 9 * (9 * S * S + 10 * 4 * S * S + 10 * 16 * S * S + 4 * 64 * S * S) + 2.0 * 9 * (4 * 64 * S * S + 64 * 3 * 64 * S * S)
+            sampling["rgb"] = {"metric": "rgb_images_per_s_4nfe_plus_taesd", "value": world * Bs / ((ms_lat + ms_dec) * 1e-3),
+                               "unit": f"{Hs}x{Hs} RGB images/s (4-NFE student + TAESD decode, clamp to [0,1]), summed over GPUs",
+                               "decode_ms_per_batch": ms_dec, "decode_images_per_s_per_gpu": Bs / (ms_dec * 1e-3),
+                               "decode_tflops_per_gpu": conv_flops * Bs / (ms_dec * 1e-3) / 1e12,
+                               "decode_share_of_sampling": ms_dec / (ms_lat + ms_dec),
+                               "image_range": [float(img.min()), float(img.max())]}
+            del vae, img
+        except Exception as e:  # the decoder is a 'next' row: its failure must not take the headline down
+            sampling["rgb"] = {"value": None, "failed": repr(e)[:300]}
 
     if rank != 0:
         if world > 1:

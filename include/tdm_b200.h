@@ -318,6 +318,27 @@ int tdm_dit_block_bwd(const TdmDitShape* s, const TdmBlockWeights* w, const TdmB
                       const void* ctx_bf16, const float* ctx_bias, const float* dx, float* dx_out, const void* ws,
                       void* scratch, void* stream);
 
+/* -------------------------------------------------------------------------------------------------
+ * TAESD decoder: diffusers.AutoencoderTiny.decode (reference main.py:166, 338; training.py:113-117), SURVEY.md 8f rank 2.
+ *   x = tanh(x / 3) * 3 ; conv3x3(4 -> 64) + ReLU ; [3 blocks ; nearest up x2 ; conv3x3(64 -> 64, no bias)] x 3 ; 1 block ;
+ *   conv3x3(64 -> 3) ; x * 2 - 1,      block(x) = ReLU(conv(ReLU(conv(ReLU(conv(x))))) + x)
+ * The 64 -> 64 convolutions run as tcgen05 implicit GEMMs over NHWC bf16 activations (TMA zero fill == padding).
+ * conv_in_w [64,4,3,3], conv_out_w [3,64,3,3] and all biases: fp32 in PyTorch layout.  block_w[i] / up_w[i]: one
+ * 64 -> 64 convolution packed as bf16 [9 taps][64 out][64 in] (tap = ky * 3 + kx); block_w holds the 10 blocks'
+ * three convolutions in order (block_b their biases), up_w the convolution that follows each upsample. */
+typedef struct TdmTaesdWeights {
+  const float* conv_in_w;  const float* conv_in_b;
+  const void* block_w[30]; const float* block_b[30];
+  const void* up_w[3];
+  const float* conv_out_w; const float* conv_out_b;
+} TdmTaesdWeights;
+/* bytes of workspace for B latents of H x W (three NHWC bf16 activation buffers at the output resolution) */
+int64_t tdm_taesd_ws_bytes(int B, int H, int W);
+/* latents [B,4,H,W] NCHW (dtype TDM_F32 / TDM_F16 / TDM_BF16) -> out fp32 [B,3,8H,8W] NCHW.  to_image != 0 applies the
+ * reference's post-processing clamp(-1, 1) * 0.5 + 0.5 (training.py:113-117) in the last kernel. */
+int tdm_taesd_decode(const TdmTaesdWeights* w, const void* latents, int latent_dtype, int B, int H, int W, float* out,
+                     int to_image, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

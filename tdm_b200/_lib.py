@@ -113,6 +113,11 @@ class TdmBlockGrads(C.Structure):
     _fields_ = [(n, vp) for n in _BLOCK_BASE + _BLOCK_LORA + ["d_tmod", "d_ctx"]]
 
 
+class TdmTaesdWeights(C.Structure):
+    _fields_ = [("conv_in_w", vp), ("conv_in_b", vp), ("block_w", vp * 30), ("block_b", vp * 30), ("up_w", vp * 3),
+                ("conv_out_w", vp), ("conv_out_b", vp)]
+
+
 ci, cl, cd, cf = C.c_int, C.c_long, C.c_double, C.c_float
 
 # name -> (restype, argtypes); every symbol include/tdm_b200.h declares must appear here
@@ -147,6 +152,8 @@ SIGNATURES = {
     "tdm_clip_coef": (ci, [vp, cf, cf, vp, vp, vp]),
     "tdm_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cd, cd, cd, cd, cd, ci, vp, vp]),
     "tdm_ema_update": (ci, [vp, vp, i64, cf, vp]),
+    "tdm_taesd_ws_bytes": (i64, [ci, ci, ci]),
+    "tdm_taesd_decode": (ci, [C.POINTER(TdmTaesdWeights), vp, ci, ci, ci, ci, vp, ci, vp, i64, vp]),
     "tdm_dit_block_ws_bytes": (i64, [C.POINTER(TdmDitShape), ci]),
     "tdm_dit_block_bwd_scratch_bytes": (i64, [C.POINTER(TdmDitShape)]),
     "tdm_dit_block_fwd": (ci, [C.POINTER(TdmDitShape), C.POINTER(TdmBlockWeights), vp, vp, vp, vp, vp, vp, ci, vp]),

@@ -317,6 +317,31 @@ def sample_4nfe(student, scheduler, noise, ctx, mask, lowp=None):
                             total_steps=1000, lowp=lowp or _models.LOWP_DTYPE)
 
 
+def save_validation_images(unet, noise_scheduler, vae, fixed_c, fixed_mask, fixed_noise, total_steps, global_step=None,
+                           output_dir=None, lowp=None):
+    """training.py:107-121: the 4-step and the 1-step student samples of the fixed prompts / noise, decoded by TAESD,
+    clamped and mapped to [0, 1].  Returns (images_4step, images_1step) fp32 [B,3,8H,8W]; written as JPEG grids like the
+    reference (fixed_4step_<step>.jpg, fixed_1step_<step>.jpg, nrow=2) when `output_dir` is given and torchvision is
+    importable (JPEG encoding is host-side I/O, outside the hot path)."""
+    from .taesd import decode_to_images
+    lowp = lowp or _models.LOWP_DTYPE
+    with torch.no_grad():
+        lat4 = generate_new(unet, noise_scheduler, fixed_noise, fixed_noise, fixed_c, fixed_mask, steps=4,
+                            total_steps=total_steps, lowp=lowp)
+        lat1 = generate_new(unet, noise_scheduler, fixed_noise, fixed_noise, fixed_c, fixed_mask, steps=1,
+                            total_steps=total_steps, lowp=lowp)
+        img4 = decode_to_images(vae, lat4)
+        img1 = decode_to_images(vae, lat1)
+    if output_dir is not None:
+        try:
+            from torchvision.utils import save_image
+            save_image(img1[:4], f"{output_dir}/fixed_1step_{global_step}.jpg", normalize=False, nrow=2)
+            save_image(img4[:4], f"{output_dir}/fixed_4step_{global_step}.jpg", normalize=False, nrow=2)
+        except ImportError:
+            torch.save({"fixed_4step": img4[:4].cpu(), "fixed_1step": img1[:4].cpu()}, f"{output_dir}/fixed_{global_step}.pt")
+    return img4, img1
+
+
 def sample_4nfe_from_host(student, scheduler, noise_host, ctx_host, mask_host, lowp=None):
     dev = student.device
     lat = sample_4nfe(student, scheduler, noise_host.to(dev, non_blocking=True), ctx_host.to(dev, non_blocking=True),
