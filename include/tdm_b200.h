@@ -318,6 +318,20 @@ int tdm_dit_block_bwd(const TdmDitShape* s, const TdmBlockWeights* w, const TdmB
                       const void* ctx_bf16, const float* ctx_bias, const float* dx, float* dx_out, const void* ws,
                       void* scratch, void* stream);
 
+/* LoRA merge for the no-grad forwards (peft semantics y = W x + (alpha / r) B A x): for every entry of a
+ * DEVICE-resident problem table, w_eff = bf16(w32 + scale * lora_b lora_a) with r = 64, one launch for the whole model.
+ * w32 / w_eff: [n_out, k_in] row-major (fp32 master / bf16 copy), lora_a: bf16 [64, k_in], lora_b: bf16 [n_out, 64];
+ * n_out and k_in multiples of 128; tile_begin = running count of 128 x 128 tiles before this problem. */
+typedef struct TdmMergeProblem {
+  const float* w32;
+  void* w_eff;
+  const void* lora_a;
+  const void* lora_b;
+  int32_t n_out, k_in;
+  int32_t tile_begin, reserved;
+} TdmMergeProblem;
+int tdm_lora_merge(const TdmMergeProblem* problems_dev, int n_problems, int total_tiles, float scale, void* stream);
+
 /* -------------------------------------------------------------------------------------------------
  * TAESD decoder: diffusers.AutoencoderTiny.decode (reference main.py:166, 338; training.py:113-117), SURVEY.md 8f rank 2.
  *   x = tanh(x / 3) * 3 ; conv3x3(4 -> 64) + ReLU ; [3 blocks ; nearest up x2 ; conv3x3(64 -> 64, no bias)] x 3 ; 1 block ;

@@ -152,6 +152,7 @@ SIGNATURES = {
     "tdm_clip_coef": (ci, [vp, cf, cf, vp, vp, vp]),
     "tdm_adamw_step": (ci, [vp, vp, vp, vp, vp, i64, cd, cd, cd, cd, cd, ci, vp, vp]),
     "tdm_ema_update": (ci, [vp, vp, i64, cf, vp]),
+    "tdm_lora_merge": (ci, [vp, ci, ci, cf, vp]),
     "tdm_taesd_ws_bytes": (i64, [ci, ci, ci]),
     "tdm_taesd_decode": (ci, [C.POINTER(TdmTaesdWeights), vp, ci, ci, ci, ci, vp, ci, vp, i64, vp]),
     "tdm_dit_block_ws_bytes": (i64, [C.POINTER(TdmDitShape), ci]),

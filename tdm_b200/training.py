@@ -244,6 +244,14 @@ class TdmTrainer:
         loss_fake, g_fake = ops.mse_loss(out_fake, eps_target)
         x0_ready = torch.cuda.Event()
         x0_ready.record(main)
+        # ---- main chain: fake-score backward.  Issued BEFORE the student's backward: the exchange runs in order on the
+        #      process group's one communication stream, and the fake-score gradients are final first (their backward
+        #      needs only the fake-score loss, the student's waits for the teacher and for x0_fake).  Issued after it, the
+        #      16 fake-score buckets (2.4 GB) queued behind the student's last bucket and ran un-overlapped at the end of
+        #      the iteration (profiles/r02_dp_timeline_2gpu_before.json: 5.7 ms exposed at 2 GPUs). ----
+        Fk.backward_impl(saved_f, g_fake, gs.hook(Fk) if gs is not None else None)
+        if gs is not None:
+            gs.finish(Fk)
         # ---- side chain, part 2: score-difference loss (main.py:514-529) on the fake-vs-teacher x0 estimates; its
         #      closed-form gradient lands on the student's x0 prediction of the step that produced the state; student
         #      backward through the solver step ----
@@ -256,14 +264,11 @@ class TdmTrainer:
                                             ptr(self.sigma_schedule), dtype_enum(self.alpha_schedule),
                                             self.alpha_schedule.numel(), ptr(d_out_s), 0, B, noise.shape[1], out_s.shape[1],
                                             noise[0, 0].numel(), stream_handle()))
-            # data parallel: every rank issues its bucketed all-reduces in the same host order (student buckets, then
-            # fake-score buckets); each one waits for the stream it was issued from
+            # data parallel: every rank issues its bucketed all-reduces in the same host order (fake-score buckets, then
+            # student buckets); each one waits for the stream it was issued from
             S.backward_impl(saved_s, d_out_s, gs.hook(S) if gs is not None else None)
             if gs is not None:
                 gs.finish(S)
-        Fk.backward_impl(saved_f, g_fake, gs.hook(Fk) if gs is not None else None)
-        if gs is not None:
-            gs.finish(Fk)
         if side is not None:
             main.wait_stream(side)
         if gs is not None:

@@ -148,6 +148,7 @@ class Transformer2DModel(nn.Module):
         self._flat16_eff = None
         self._eff_key = None
         self._merged_structs = None
+        self._merge_table = None
         self._update_count = 0
 
     # ------------------------------------------------------------------ parameters
@@ -205,7 +206,7 @@ class Transformer2DModel(nn.Module):
             self._pos_cache = {}
             self._anchor = torch.zeros((), device=new.device, requires_grad=True)
             self._flat16 = self._grad = self._lflat16 = self._lgrad = None
-            self._flat16_eff = self._eff_key = self._merged_structs = None
+            self._flat16_eff = self._eff_key = self._merged_structs = self._merge_table = None
             self._flat16_version = self._lflat16_version = -1
             self._scratch = self._infer_ws = None
             self._bind_params()
@@ -300,7 +301,7 @@ class Transformer2DModel(nn.Module):
             if ".lora_" in n:
                 p.requires_grad_(True)
         self._lflat16 = self._lgrad = None
-        self._flat16_eff = self._eff_key = self._merged_structs = None
+        self._flat16_eff = self._eff_key = self._merged_structs = self._merge_table = None
         return self
 
     def peft_state_dict(self, adapter_name="default"):
@@ -445,17 +446,12 @@ class Transformer2DModel(nn.Module):
         self._sync_bf16()
         if self._flat16_eff is None:
             self._flat16_eff = torch.empty_like(self._flat16)
-            self._merged_structs = None
+            self._merged_structs = self._merge_table = None
         self._flat16_eff.copy_(self._flat16)
-        LA = self._lora_arena
-        for i in range(self.depth):
-            b = f"transformer_blocks.{i}."
-            for t in self.lora_targets:
-                an, bn = b + t + ".lora_A.default.weight", b + t + ".lora_B.default.weight"
-                w32 = self._arena.view(self._flat, b + t + ".weight")
-                weff = self._arena.view(self._flat16_eff, b + t + ".weight")
-                ops.gemm(LA.view(self._lflat16, bn), LA.view(self._lflat16, an), b_mn_major=True, alpha=self.lora_scale,
-                         res=w32, out_bf16=weff)
+        if self._merge_table is None:
+            self._build_merge_table()
+        table, n_prob, n_tiles = self._merge_table
+        check(_lib.lib().tdm_lora_merge(ptr(table), n_prob, n_tiles, float(self.lora_scale), stream_handle()))
         self._eff_key = key
         if self._merged_structs is None:
             ws = []
@@ -470,6 +466,27 @@ class Transformer2DModel(nn.Module):
                     setattr(w, "b_" + field, ptr(self._w32(b + wname + ".bias")))
                 ws.append(w)
             self._merged_structs = ws
+
+    def _build_merge_table(self):
+        """Device-side table of (fp32 master, merged bf16 copy, LoRA A, LoRA B, shape) for every adapted linear: the arenas
+        never move, so it is built once (TdmMergeProblem, include/tdm_b200.h)."""
+        import struct
+        LA = self._lora_arena
+        rows, tile = [], 0
+        for i in range(self.depth):
+            b = f"transformer_blocks.{i}."
+            for t in self.lora_targets:
+                an, bn = b + t + ".lora_A.default.weight", b + t + ".lora_B.default.weight"
+                w32 = self._arena.view(self._flat, b + t + ".weight")
+                weff = self._arena.view(self._flat16_eff, b + t + ".weight")
+                n_out, k_in = w32.shape
+                if n_out % 128 or k_in % 128:
+                    raise _lib.TdmError("LoRA merge needs weight dimensions that are multiples of 128")
+                rows.append(struct.pack("<QQQQiiii", w32.data_ptr(), weff.data_ptr(), LA.view(self._lflat16, an).data_ptr(),
+                                        LA.view(self._lflat16, bn).data_ptr(), n_out, k_in, tile, 0))
+                tile += (n_out // 128) * (k_in // 128)
+        raw = torch.frombuffer(bytearray(b"".join(rows)), dtype=torch.uint8).to(self.device)
+        self._merge_table = (raw, len(rows), tile)
 
     def _shape(self, B, N, L, lora=True):
         s = _lib.TdmDitShape()
