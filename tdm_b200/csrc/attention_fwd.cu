@@ -196,7 +196,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int dk16 = p.dk16;
     // (one polling lane + __syncwarp instead of 32 polling lanes shortened the waits in the clock64 trace but measured
     // slower end to end: 100 vs 91 us)
-    auto wait1 = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
+    auto wait1 = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr (DBG & 4096) {  // experiment: one polling lane in the MMA warp only
+        if (lane == 0) mbar_wait(bar, parity);
+        __syncwarp();
+      } else {
+        mbar_wait(bar, parity);
+      }
+    };
     // running tile coordinates of the two issue streams (no integer divisions on the issue path)
     struct Cur { int it, j, st; uint32_t ph; };
     auto advance = [&](Cur& c) {
@@ -497,6 +504,7 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
     case 512: kern = attn_fwd_kernel<512>; break;
     case 927: kern = attn_fwd_kernel<927>; break;
     case 1024: kern = attn_fwd_kernel<1024>; break;
+    case 4096: kern = attn_fwd_kernel<4096>; break;
     default: break;
   }
   int threads = FWD_THREADS;
