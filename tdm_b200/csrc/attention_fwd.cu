@@ -64,7 +64,7 @@ constexpr int FWD_THREADS = 352;  // 8 softmax warps + Q/K TMA warp + MMA warp +
 // DBG != 0 instantiations are timing ablations (scripts/attn_ablate.py; results are WRONG by construction):
 //   1 no MUFU (ex2 replaced by a move)   2 no half-row maxima exchange   4 no P store to TMEM   8 no S load from TMEM
 //   16 no running-max loop   64 clock64 trace   128 no P V MMAs   256 no Q K^T MMAs   512 no K / V TMA loads
-//   1024 (stays correct) every second odd exponential as a degree-3 polynomial on the FMA pipe: measured no faster
+// (a variant with every fourth exponential as a degree-3 polynomial on the FMA pipe measured no faster: 90.4 vs 88.8 us)
 // What they showed (profiles/r02_attn_ablation*.jsonl, r02_attn_trace_*.txt): with EVERY MMA, TMA load and softmax
 // instruction removed (927) the kernel still takes 83 of 88 us -- the loop is bound by the latency of its own
 // mbarrier / tcgen05.commit hand-offs (300-900 clk per hop, two hops per tile on the critical cycle), not by the
@@ -195,15 +195,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t stage_step = uint32_t(tile_bytes) >> 4;  // descriptor address field counts 16-byte units
     const int dk16 = p.dk16;
     // (one polling lane + __syncwarp instead of 32 polling lanes shortened the waits in the clock64 trace but measured
-    // slower end to end: 100 vs 91 us)
-    auto wait1 = [&](uint64_t* bar, uint32_t parity) {
-      if constexpr (DBG & 4096) {  // experiment: one polling lane in the MMA warp only
-        if (lane == 0) mbar_wait(bar, parity);
-        __syncwarp();
-      } else {
-        mbar_wait(bar, parity);
-      }
-    };
+    // slower end to end: 100 vs 91 us in every warp, 92.6 vs 86.5 us in this warp alone)
+    auto wait1 = [&](uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); };
     // running tile coordinates of the two issue streams (no integer divisions on the issue path)
     struct Cur { int it, j, st; uint32_t ph; };
     auto advance = [&](Cur& c) {
@@ -376,15 +369,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         } else {
           const float nm = -m_used;
           auto ex = [](float x) { if constexpr (DBG & 1) return x; else return ex2_fast(x); };
-          auto exq = [](float x, int i) {  // DBG & 1024: one exponential in four as a degree-3 polynomial on the FMA pipe
-            if constexpr (DBG & 1024) return (i & 1) ? ex2_poly(x) : ex2_fast(x);
-            else if constexpr (DBG & 1) return x;
-            else return ex2_fast(x);
-          };
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float p0 = ex(fmaf(__uint_as_float(sr[2 * i]), p.scale_log2, nm));
-            const float p1 = exq(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm), i);
+            const float p1 = ex(fmaf(__uint_as_float(sr[2 * i + 1]), p.scale_log2, nm));
             l0 += p0;
             l1 += p1;
             sr[i] = pack_bf16(p0, p1);
@@ -503,8 +491,6 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
     case 415: kern = attn_fwd_kernel<415>; break;
     case 512: kern = attn_fwd_kernel<512>; break;
     case 927: kern = attn_fwd_kernel<927>; break;
-    case 1024: kern = attn_fwd_kernel<1024>; break;
-    case 4096: kern = attn_fwd_kernel<4096>; break;
     default: break;
   }
   int threads = FWD_THREADS;
