@@ -448,6 +448,8 @@ int make_head_map(CUtensorMap* map, const void* ptr, int B, int S, int H, int d,
   return make_tma_bf16(map, ptr, 4, dims, strides, box, TMA_SWZ_128);
 }
 
+int launch_attn_fwd2(const TdmAttn* a, void* stream);  // attention_fwd2.cu: two query tiles per CTA, head_dim <= 96
+
 }  // namespace tdm
 
 using namespace tdm;
@@ -461,6 +463,9 @@ extern "C" int tdm_attn_fwd(const TdmAttn* a, void* stream) {
                   a->v_stride_s % 8 == 0 && a->v_stride_h % 8 == 0 && a->v_stride_b % 8 == 0 &&
                   a->o_stride_s % 8 == 0 && a->o_stride_h % 8 == 0 && a->o_stride_b % 8 == 0,
               "tdm_attn_fwd: strides must be multiples of 8 elements (16 bytes)");
+  // head_dim <= 96: the two-stream kernel (TDM_B200_ATTN_V1=1 keeps this file's one-tile kernel for A/B timing)
+  const bool force_v1 = getenv("TDM_B200_ATTN_V1") && atoi(getenv("TDM_B200_ATTN_V1")) != 0;
+  if (a->d <= 96 && !force_v1 && !getenv("TDM_B200_ATTN_DBG")) return launch_attn_fwd2(a, stream);
   CUtensorMap tmQ, tmK, tmV;
   int rc;
   if ((rc = make_head_map(&tmQ, a->Q, a->B, a->Sq, a->H, a->d, a->q_stride_b, a->q_stride_s, a->q_stride_h))) return rc;

@@ -172,6 +172,46 @@ def test_attention_fwd_bwd(B, H, Sq, Sk, d, cross):
     assert _rel(dq, qf.grad) < 2e-2, "dQ"
 
 
+@pytest.mark.parametrize("B,H,Sq,Sk,d,cross,big", [
+    (2, 16, 1024, 1024, 72, False, False),
+    (2, 16, 1024, 120, 72, True, False),
+    (1, 2, 200, 77, 72, True, False),     # ragged: second query tile of the pair partly / fully out of range
+    (1, 3, 130, 250, 96, True, False),
+    (1, 2, 384, 300, 40, True, False),
+    (3, 5, 640, 384, 64, False, False),   # odd item count: CTAs with different numbers of items
+    (2, 4, 512, 1024, 72, False, True),   # row maxima that grow by far more than 2^8 between tiles: the lazy-rescale path
+])
+def test_attention_fwd_two_stream_kernel_matches_one_tile_kernel(B, H, Sq, Sk, d, cross, big, monkeypatch):
+    """attention_fwd2.cu (two query tiles per CTA, default for head_dim <= 96) against attention_fwd.cu
+    (TDM_B200_ATTN_V1=1) and the fp32 reference: same softmax arithmetic (same maxima, same exponentials, same bf16 P),
+    so the outputs agree to the last bf16 bit or very nearly; both are within the forward tolerance of the reference."""
+    from tdm_b200 import ops
+    torch.manual_seed(5)
+    q = torch.randn(B, Sq, H, d, device="cuda").bfloat16()
+    k = torch.randn(B, Sk, H, d, device="cuda").bfloat16()
+    v = torch.randn(B, Sk, H, d, device="cuda").bfloat16()
+    if big:
+        k[:, Sk // 2:] *= 6.0
+    bias = None
+    if cross:
+        lens = torch.randint(1, Sk + 1, (B,), device="cuda")
+        bias = (1 - (torch.arange(Sk, device="cuda")[None] < lens[:, None]).float()) * -10000.0
+    outs = {}
+    for v1 in ("1", "0"):
+        monkeypatch.setenv("TDM_B200_ATTN_V1", v1)
+        o = torch.full((B, Sq, H, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+        lse = torch.full((B, H, Sq), float("nan"), device="cuda")
+        ops.attn_fwd(q, k, v, o, d ** -0.5, bias=bias, lse=lse)
+        torch.cuda.synchronize()
+        outs[v1] = (o, lse)
+    o_ref, lse_ref = _attn_ref(q.float(), k.float(), v.float(), d ** -0.5, bias)
+    for o, lse in outs.values():
+        assert _rel(o, o_ref) < 1e-2
+        assert (lse - lse_ref).abs().max().item() < 2e-3
+    assert (outs["0"][0].float() - outs["1"][0].float()).abs().max().item() <= 2e-2 * o_ref.abs().max().item() / 4
+    assert (outs["0"][1] - outs["1"][1]).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("B,H,S,d", [(2, 16, 1024, 72), (8, 16, 1024, 72)])
 def test_attention_fwd_is_deterministic_with_cold_loads(B, H, S, d):
     """Regression for the P V completion barrier of attn_fwd_kernel: with one barrier for every tile, a parity wait could
