@@ -15,9 +15,13 @@ constexpr int CHUNK = 128 * 128;  // bytes of one [128 rows x 64 bf16] swizzled 
 
 int make_head_map(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
                   long stride_h);
+int make_head_map64(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
+                    long stride_h);  // attention_fwd2.cu: box 32 x 128, 64-byte swizzle
+constexpr int CH64 = 128 * 64;  // one [128 rows x 32 bf16] chunk, 64-byte swizzle
 
 struct AttnBwdParams {
   int B, H, Sq, Sk, d, nd, dk16;
+  int nc;  // ceil(d / 32): chunks of the 64-byte-swizzled tiles (attn_bwd_kernel)
   float scale, scale_log2;
   const float* bias;   // [B, Sk] or null
   const float* lse;    // [B, H, Sq]
@@ -292,8 +296,13 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 
 // ------------------------------------------------------------------------------------------------
 // Pipelined backward for head_dim <= 80 (PixArt: 72).  Same math as above, but
-//   * dQ has its own TMEM columns and is drained by a SECOND warpgroup with 16-byte vector reds, so the drain
-//     overlaps the next query tile;
+//   * dQ has its own TMEM columns and is drained by a SECOND warpgroup, so the drain overlaps the next query tile: each
+//     drain warp stages its 32 query rows (fp32) in shared memory and ONE TMA reduce-add per warp and tile adds them into
+//     the accumulator.  (Thread-per-row red.global.add.v4.f32 -- 32 rows = 32 transactions per instruction, 2300 per tile
+//     -- clogged the SM's load/store queue, which every mbarrier wait and tcgen05.ld of the CTA shares; found in the
+//     forward kernel, attention_fwd2.cu.)  dK / dV leave through shared memory and TMA stores for the same reason;
+//   * Q / K / V / dO tiles use rows of 64 bytes (32 head-dim columns, 64-byte swizzle): 24 KB per tile for head_dim 72
+//     instead of 32 KB, which is what makes room for the dQ staging buffer;
 //   * Q / dO tiles are double-buffered in shared memory and the TMA producer runs one tile ahead;
 //   * P^T (bf16) is written back into the S^T columns and feeds dV += P^T dO straight from tensor memory;
 //   * dP^T of the next tile is issued as soon as the compute warps have pulled the current S^T / dP^T into
@@ -307,17 +316,19 @@ constexpr int BWD_THREADS = 448;  // 8 compute warps (two halves of the query co
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
+                const __grid_constant__ CUtensorMap tmdV, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SW128 tiles need 1024-byte alignment
-  const int tile_bytes = p.nd * CHUNK;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-byte alignment
+  const int tile_bytes = p.nc * CH64;
   uint8_t* sK = smem;
   uint8_t* sV = sK + tile_bytes;
   uint8_t* sQ = sV + tile_bytes;          // 2 stages
   uint8_t* sdO = sQ + 2 * tile_bytes;     // 2 stages
-  uint8_t* sdSt = sdO + 2 * tile_bytes;   // [128 keys x 128 queries] bf16, 2 chunks
-  float* sLse = reinterpret_cast<float*>(sdSt + 2 * CHUNK);  // 2 x 128 (log2 units)
+  uint8_t* sdSt = sdO + 2 * tile_bytes;   // [128 keys x 128 queries] bf16, 2 chunks of 64 columns, 128-byte swizzle
+  float* sdQ = reinterpret_cast<float*>(sdSt + 2 * CHUNK);   // [128 queries][d] fp32 staging of the dQ tile
+  float* sLse = sdQ + 128 * p.d;                             // 2 x 128 (log2 units)
   float* sDelta = sLse + 256;                                 // 2 x 128
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* kv_full = bars;        // 1
@@ -363,17 +374,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmdO);
       mbar_arrive_expect_tx(kv_full, 2 * tile_bytes);
-      for (int c = 0; c < p.nd; ++c) {
-        tma_load_4d(sK + c * CHUNK, &tmK, kv_full, c * 64, k0, h, b);
-        tma_load_4d(sV + c * CHUNK, &tmV, kv_full, c * 64, k0, h, b);
+      for (int c = 0; c < p.nc; ++c) {
+        tma_load_4d(sK + c * CH64, &tmK, kv_full, c * 32, k0, h, b);
+        tma_load_4d(sV + c * CH64, &tmV, kv_full, c * 32, k0, h, b);
       }
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait_relaxed(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * tile_bytes);
-        for (int c = 0; c < p.nd; ++c) {
-          tma_load_4d(sQ + st * tile_bytes + c * CHUNK, &tmQ, &qdo_full[st], c * 64, i * 128, h, b);
-          tma_load_4d(sdO + st * tile_bytes + c * CHUNK, &tmdO, &qdo_full[st], c * 64, i * 128, h, b);
+        for (int c = 0; c < p.nc; ++c) {
+          tma_load_4d(sQ + st * tile_bytes + c * CH64, &tmQ, &qdo_full[st], c * 32, i * 128, h, b);
+          tma_load_4d(sdO + st * tile_bytes + c * CH64, &tmdO, &qdo_full[st], c * 32, i * 128, h, b);
         }
       }
     }
@@ -383,13 +394,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t id_kk = make_idesc_bf16(128, 128, 0, 0);    // S^T, dP^T : A K-major, B K-major
     const uint32_t id_kmn = make_idesc_bf16(128, dpad, 0, 1);  // dV, dK    : A K-major (TMEM / smem), B MN-major
     const uint32_t id_mnmn = make_idesc_bf16(128, dpad, 1, 1); // dQ        : A MN-major, B MN-major
-    const uint64_t dK_k = make_sdesc_sw128(smem_u32(sK), 16, 1024);       // K as K-major operand (S^T)
-    const uint64_t dV_k = make_sdesc_sw128(smem_u32(sV), 16, 1024);       // V as K-major operand (dP^T)
-    const uint64_t dK_mn = make_sdesc_sw128(smem_u32(sK), CHUNK, 1024);   // K as MN-major operand (dQ)
-    const uint64_t dQ_k0 = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
-    const uint64_t dQ_mn0 = make_sdesc_sw128(smem_u32(sQ), CHUNK, 1024);
-    const uint64_t ddO_k0 = make_sdesc_sw128(smem_u32(sdO), 16, 1024);
-    const uint64_t ddO_mn0 = make_sdesc_sw128(smem_u32(sdO), CHUNK, 1024);
+    // Q / K / V / dO tiles: 64-byte swizzle.  K-major: 8-row groups 512 bytes apart, two 16-column k-steps per 32-column
+    // chunk; MN-major: chunks CH64 apart, one k-step = 16 rows of 64 bytes.
+    const uint64_t dK_k = make_sdesc_sw64(smem_u32(sK), 16, 512);       // K as K-major operand (S^T)
+    const uint64_t dV_k = make_sdesc_sw64(smem_u32(sV), 16, 512);       // V as K-major operand (dP^T)
+    const uint64_t dK_mn = make_sdesc_sw64(smem_u32(sK), CH64, 512);    // K as MN-major operand (dQ)
+    const uint64_t dQ_k0 = make_sdesc_sw64(smem_u32(sQ), 16, 512);
+    const uint64_t dQ_mn0 = make_sdesc_sw64(smem_u32(sQ), CH64, 512);
+    const uint64_t ddO_k0 = make_sdesc_sw64(smem_u32(sdO), 16, 512);
+    const uint64_t ddO_mn0 = make_sdesc_sw64(smem_u32(sdO), CH64, 512);
     const uint64_t ddS_k = make_sdesc_sw128(smem_u32(sdSt), 16, 1024);
     const uint64_t ddS_mn = make_sdesc_sw128(smem_u32(sdSt), CHUNK, 1024);
     const uint32_t stage_step = uint32_t(tile_bytes) >> 4;
@@ -399,7 +412,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 5; ++k)
         if (k < dk16) {
-          const uint32_t off = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
+          const uint32_t off = ((k >> 1) * CH64 + (k & 1) * 32) >> 4;
           umma_bf16(tm_St, dK_k + off, qd + off, id_kk, k != 0);
         }
     };
@@ -408,7 +421,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 5; ++k)
         if (k < dk16) {
-          const uint32_t off = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
+          const uint32_t off = ((k >> 1) * CH64 + (k & 1) * 32) >> 4;
           umma_bf16(tm_dPt, dV_k + off, od + off, id_kk, k != 0);
         }
     };
@@ -436,7 +449,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t od_mn = ddO_mn0 + uint64_t(st * stage_step), qd_mn = dQ_mn0 + uint64_t(st * stage_step);
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV += P^T dO : contraction over the 128 queries, A from tensor memory
-          umma_bf16_ts(tm_dV, tm_St + (k >> 2) * 64 + (k & 3) * 8, od_mn + uint64_t(k * (2048 >> 4)), id_kmn, (i | k) != 0);
+          umma_bf16_ts(tm_dV, tm_St + (k >> 2) * 64 + (k & 3) * 8, od_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
         if (i + 1 < n_q) {
           issue_st(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
           umma_commit(sdp_full);
@@ -444,7 +457,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dK += dS^T Q
           const uint32_t offA = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
-          umma_bf16(tm_dK, ddS_k + offA, qd_mn + uint64_t(k * (2048 >> 4)), id_kmn, (i | k) != 0);
+          umma_bf16(tm_dK, ddS_k + offA, qd_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
         }
       }
       __syncwarp();
@@ -455,7 +468,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dQ = dS K : contraction over the 128 keys; A = dS^T read MN-major
-          umma_bf16(tm_dQ, ddS_mn + uint64_t(k * (2048 >> 4)), dK_mn + uint64_t(k * (2048 >> 4)), id_mnmn, k != 0);
+          umma_bf16(tm_dQ, ddS_mn + uint64_t(k * (2048 >> 4)), dK_mn + uint64_t(k * (1024 >> 4)), id_mnmn, k != 0);
         umma_commit(dq_full);
         umma_commit(&qdo_empty[st]);
       }
@@ -531,47 +544,76 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // epilogue: warps 0-3 write dV, warps 4-7 write dK of this key tile (thread == key row)
     mbar_wait(dq_full, (n_q - 1) & 1);
     tc_fence_after();
-    bf16* out_row = wg == 0 ? p.dV + (long)b * p.dv_stride_b + (long)kv * p.dv_stride_s + (long)h * p.dv_stride_h
-                            : p.dK + (long)b * p.dk_stride_b + (long)kv * p.dk_stride_s + (long)h * p.dk_stride_h;
+    // dV (warps 0-3) / dK (warps 4-7): each warp stages its 32 key rows as bf16 in the Q buffers (free: dq_full of the
+    // last tile means every MMA has retired) and stores them with one TMA store; rows >= Sk are clipped by the map.
     const uint32_t tm_src = wg == 0 ? tm_dV : tm_dK;
     const float osc = wg == 0 ? 1.f : p.scale;
-    for (int c = 0; c < p.d; c += 8) {
-      uint32_t r[8];
-      tmem_ld8(tm_src + lane_off + c, r);
+    uint8_t* stage = sQ + wg * tile_bytes + (warp & 3) * (32 * p.d * 2);
+    uint8_t* srow = stage + lane * (p.d * 2);
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {  // d <= 80: 48 + 32 columns, one tcgen05.ld round each
+      uint32_t r[3][16];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (3 * hh + i < p.dk16) tmem_ld16(tm_src + lane_off + 16 * (3 * hh + i), r[i]);
       tmem_ld_wait();
-      if (kv < p.Sk) {
-        uint4 w;
-        w.x = pack_bf16(__uint_as_float(r[0]) * osc, __uint_as_float(r[1]) * osc);
-        w.y = pack_bf16(__uint_as_float(r[2]) * osc, __uint_as_float(r[3]) * osc);
-        w.z = pack_bf16(__uint_as_float(r[4]) * osc, __uint_as_float(r[5]) * osc);
-        w.w = pack_bf16(__uint_as_float(r[6]) * osc, __uint_as_float(r[7]) * osc);
-        *reinterpret_cast<uint4*>(out_row + c) = w;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        if (8 * (6 * hh + i) < p.d) {
+#define BW_E(k_) (__uint_as_float(r[i >> 1][(i & 1) * 8 + (k_)]) * osc)
+          uint4 w;
+          w.x = pack_bf16(BW_E(0), BW_E(1));
+          w.y = pack_bf16(BW_E(2), BW_E(3));
+          w.z = pack_bf16(BW_E(4), BW_E(5));
+          w.w = pack_bf16(BW_E(6), BW_E(7));
+#undef BW_E
+          *reinterpret_cast<uint4*>(srow + 16 * (6 * hh + i)) = w;
+        }
       }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_4d(wg == 0 ? &tmdV : &tmdK, stage, 0, k0 + (warp & 3) * 32, h, b);
+      tma_store_commit();
+      tma_store_wait_all();
     }
   } else {
     // ===================== dQ drain (128 threads, thread == query row) =====================
-    const int tid = threadIdx.x - 256;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    float* stage = sdQ + (warp & 3) * 32 * p.d;  // this warp's 32 query rows, dense [32][d] fp32
+    float* srow = stage + lane * p.d;
+    if (lane == 0) tma_prefetch_desc(&tmdQ);
     for (int i = 0; i < n_q; ++i) {
-      const int q = i * 128 + tid;
       mbar_wait_relaxed(dq_full, i & 1);
       tc_fence_after();
-      float* dq_row = p.dq_accum + (((long)b * p.Sq + q) * p.H + h) * p.d;
-      for (int c = 0; c < p.d; c += 8) {
-        uint32_t r[8];
-        tmem_ld8(tm_dQ + lane_off + c, r);
-        tmem_ld_wait();
-        if (q < p.Sq) {
-          red_add_v4(dq_row + c, __uint_as_float(r[0]) * p.scale, __uint_as_float(r[1]) * p.scale,
-                     __uint_as_float(r[2]) * p.scale, __uint_as_float(r[3]) * p.scale);
-          red_add_v4(dq_row + c + 4, __uint_as_float(r[4]) * p.scale, __uint_as_float(r[5]) * p.scale,
-                     __uint_as_float(r[6]) * p.scale, __uint_as_float(r[7]) * p.scale);
-        }
-      }
+      uint32_t r[5][16];  // d <= 80: one tcgen05.ld round
+#pragma unroll
+      for (int c = 0; c < 5; ++c)
+        if (c < p.dk16) tmem_ld16(tm_dQ + lane_off + 16 * c, r[c]);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(dq_free);
+      if (lane == 0) {
+        mbar_arrive(dq_free);                // dQ is in registers: the next tile's dQ may be issued
+        if (i > 0) tma_store_wait_read();    // the previous tile's reduce has read the staging rows
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 20; ++c) {
+        if (4 * c < p.d)
+          *reinterpret_cast<float4*>(srow + 4 * c) =
+              make_float4(__uint_as_float(r[c >> 2][(c & 3) * 4]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 1]) * p.scale,
+                          __uint_as_float(r[c >> 2][(c & 3) * 4 + 2]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 3]) * p.scale);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {  // rows >= Sq are clipped by the map
+        tma_reduce_add_3d(&tmdQ, stage, h * p.d, i * 128 + (warp & 3) * 32, b);
+        tma_store_commit();
+      }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -635,15 +677,33 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   p.dK = (bf16*)a->dK; p.dk_stride_b = a->dk_stride_b; p.dk_stride_s = a->dk_stride_s; p.dk_stride_h = a->dk_stride_h;
   p.dV = (bf16*)a->dV; p.dv_stride_b = a->dv_stride_b; p.dv_stride_s = a->dv_stride_s; p.dv_stride_h = a->dv_stride_h;
   dim3 grid((a->Sk + 127) / 128, a->H, a->B);
+  p.nc = (a->d + 31) / 32;
   if (p.dk16 * 16 <= 80 && (((long)a->H * a->d) % 4 == 0) && (a->d % 4 == 0)) {
-    const int smem = 6 * p.nd * CHUNK + 2 * CHUNK + 2048 + 256;
+    if ((rc = make_head_map64(&tmQ, a->Q, a->B, a->Sq, a->H, a->d, a->q_stride_b, a->q_stride_s, a->q_stride_h))) return rc;
+    if ((rc = make_head_map64(&tmK, a->K, a->B, a->Sk, a->H, a->d, a->k_stride_b, a->k_stride_s, a->k_stride_h))) return rc;
+    if ((rc = make_head_map64(&tmV, a->V, a->B, a->Sk, a->H, a->d, a->v_stride_b, a->v_stride_s, a->v_stride_h))) return rc;
+    if ((rc = make_head_map64(&tmdO, a->dO, a->B, a->Sq, a->H, a->d, a->o_stride_b, a->o_stride_s, a->o_stride_h))) return rc;
+    CUtensorMap tmdQ, tmdK, tmdV;
+    {  // fp32 accumulator [B, Sq, H*d]: one 32-row x d box per drain warp; bf16 dK / dV views [B, Sk, H, d]
+      uint64_t dims[3] = {(uint64_t)HD, (uint64_t)a->Sq, (uint64_t)a->B};
+      uint64_t strides[2] = {(uint64_t)HD * 4, (uint64_t)a->Sq * HD * 4};
+      uint32_t box[3] = {(uint32_t)a->d, 32, 1};
+      if ((rc = make_tma_typed(&tmdQ, a->dq_accum, 1, 3, dims, strides, box, TMA_SWZ_NONE))) return rc;
+      uint64_t dims4[4] = {(uint64_t)a->d, (uint64_t)a->Sk, (uint64_t)a->H, (uint64_t)a->B};
+      uint32_t box4[4] = {(uint32_t)a->d, 32, 1, 1};
+      uint64_t sk[3] = {(uint64_t)a->dk_stride_s * 2, (uint64_t)a->dk_stride_h * 2, (uint64_t)a->dk_stride_b * 2};
+      if ((rc = make_tma_bf16(&tmdK, a->dK, 4, dims4, sk, box4, TMA_SWZ_NONE))) return rc;
+      uint64_t sv[3] = {(uint64_t)a->dv_stride_s * 2, (uint64_t)a->dv_stride_h * 2, (uint64_t)a->dv_stride_b * 2};
+      if ((rc = make_tma_bf16(&tmdV, a->dV, 4, dims4, sv, box4, TMA_SWZ_NONE))) return rc;
+    }
+    const int smem = 6 * p.nc * CH64 + 2 * CHUNK + 128 * a->d * 4 + 2048 + 256;
     static int smem_set = 0;
     if (smem > smem_set) {
       TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       smem_set = smem;
     }
     ::tdm::count_launch();
-    TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, p));
+    TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
   } else {
     const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
     static int smem_set_w = 0;

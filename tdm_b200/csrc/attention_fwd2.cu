@@ -424,7 +424,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 // 4-D tensor map over a [B, S, H, d] view (d contiguous); box = 32 x 128 x 1 x 1, 64-byte swizzle.
-static int make_head_map64(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
+int make_head_map64(CUtensorMap* map, const void* ptr, int B, int S, int H, int d, long stride_b, long stride_s,
                            long stride_h) {
   uint64_t dims[4] = {(uint64_t)d, (uint64_t)S, (uint64_t)H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)stride_s * 2, (uint64_t)stride_h * 2, (uint64_t)stride_b * 2};
