@@ -7,6 +7,7 @@
 // Operand reuse without copies: the Q / dO tiles are read K-major for S^T / dP^T and MN-major for
 // dK / dV; dS^T in shared memory is read K-major for dK and MN-major (as dS) for dQ.
 // TMEM: S^T [0,128) (reused for dQ), dP^T [128,256), dV [256,384), dK [384,512).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tdm {
@@ -31,6 +32,7 @@ struct AttnBwdParams {
   long dk_stride_b, dk_stride_s, dk_stride_h;
   bf16* dV;
   long dv_stride_b, dv_stride_s, dv_stride_h;
+  long long* trace;  // TDM_B200_ATTN_TRACE: clock64 stamps of CTA (0,0,0), [query tile][16 events]
 };
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]; the same kernel zero-fills the fp32 dQ accumulator (layout
@@ -313,6 +315,13 @@ attn_bwd_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 // ------------------------------------------------------------------------------------------------
 constexpr int BWD_THREADS = 448;  // 8 compute warps (two halves of the query columns) + 4 drain warps + TMA + MMA
 
+#define BW_TRACE(i_, e_)                                                                       \
+  do {                                                                                         \
+    if constexpr (TRACE) {                                                                     \
+      if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i_) < 32) p.trace[(i_) * 16 + (e_)] = clock64(); \
+    }                                                                                          \
+  } while (0)
+template <bool TRACE>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -380,7 +389,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
-        mbar_wait_relaxed(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&qdo_full[st], 2 * tile_bytes);
         for (int c = 0; c < p.nc; ++c) {
           tma_load_4d(sQ + st * tile_bytes + c * CH64, &tmQ, &qdo_full[st], c * 32, i * 128, h, b);
@@ -443,8 +452,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (elect_one()) issue_dpt(i + 1);
         __syncwarp();
       }
+      if (lane == 0) BW_TRACE(i, 0);
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
+      if (lane == 0) BW_TRACE(i, 1);
       if (elect_one()) {
         const uint64_t od_mn = ddO_mn0 + uint64_t(st * stage_step), qd_mn = dQ_mn0 + uint64_t(st * stage_step);
 #pragma unroll
@@ -459,20 +470,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t offA = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
           umma_bf16(tm_dK, ddS_k + offA, qd_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
         }
+        // dK(i) is the last reader of Q(i), dV(i) of dO(i): the stage is released HERE, not behind dQ(i) -- the reload
+        // (tile i+2) has a ~2500 clk round trip and the loop was waiting for it (clock64 trace, profiles/)
+        umma_commit(&qdo_empty[st]);
       }
       __syncwarp();
+      if (lane == 0) BW_TRACE(i, 2);
       if (i > 0) {
         mbar_wait(dq_free, (i - 1) & 1);
         tc_fence_after();
       }
+      if (lane == 0) BW_TRACE(i, 3);
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dQ = dS K : contraction over the 128 keys; A = dS^T read MN-major
           umma_bf16(tm_dQ, ddS_mn + uint64_t(k * (2048 >> 4)), dK_mn + uint64_t(k * (1024 >> 4)), id_mnmn, k != 0);
         umma_commit(dq_full);
-        umma_commit(&qdo_empty[st]);
       }
       __syncwarp();
+      if (lane == 0) BW_TRACE(i, 4);
     }
   } else if (warp < 8) {
     // ===================== P / dS compute (2 x 128 threads, thread == key row) =====================
@@ -495,8 +511,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (wg == 0) lse_s[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
       else del_s[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) BW_TRACE(i, 5);
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
+      if (threadIdx.x == 0) BW_TRACE(i, 6);
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int c = wg * 2 + cc;
@@ -527,7 +545,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         // P^T packed into this warpgroup's OWN half of the S^T columns ([0,32) / [64,96)): never passes the columns
         // it still has to read, and never touches the other warpgroup's
         tmem_st16(tm_St + lane_off + wg * 64 + cc * 16, pk);
+        if (threadIdx.x == 0 && cc == 0) BW_TRACE(i, 7);
         if (cc == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
+        if (threadIdx.x == 0 && cc == 0) BW_TRACE(i, 8);
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           const int U = c * 4 + u4;
@@ -540,6 +560,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (threadIdx.x == 0) BW_TRACE(i, 9);
     }
     // epilogue: warps 0-3 write dV, warps 4-7 write dK of this key tile (thread == key row)
     mbar_wait(dq_full, (n_q - 1) & 1);
@@ -587,6 +608,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < n_q; ++i) {
       mbar_wait_relaxed(dq_full, i & 1);
       tc_fence_after();
+      if (threadIdx.x == 256) BW_TRACE(i, 10);
       uint32_t r[5][16];  // d <= 80: one tcgen05.ld round
 #pragma unroll
       for (int c = 0; c < 5; ++c)
@@ -612,6 +634,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_reduce_add_3d(&tmdQ, stage, h * p.d, i * 128 + (warp & 3) * 32, b);
         tma_store_commit();
       }
+      if (threadIdx.x == 256) BW_TRACE(i, 11);
     }
     if (lane == 0) tma_store_wait_all();
   }
@@ -699,11 +722,38 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
     const int smem = 6 * p.nc * CH64 + 2 * CHUNK + 128 * a->d * 4 + 2048 + 256;
     static int smem_set = 0;
     if (smem > smem_set) {
-      TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       smem_set = smem;
     }
+    p.trace = nullptr;
+    const char* trace_path = getenv("TDM_B200_ATTN_TRACE");  // debugging aid: per-tile clock64 stamps of CTA (0,0,0)
+    static long long* trace_buf = nullptr;
+    if (trace_path && *trace_path) {
+      if (!trace_buf) TDM_CHECK_CUDA(cudaMalloc(&trace_buf, 32 * 16 * sizeof(long long)));
+      TDM_CHECK_CUDA(cudaMemsetAsync(trace_buf, 0, 32 * 16 * sizeof(long long), s));
+      p.trace = trace_buf;
+    }
     ::tdm::count_launch();
-    TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
+    if (p.trace) TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
+    else TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
+    if (p.trace) {
+      static long long host[32 * 16];
+      TDM_CHECK_CUDA(cudaStreamSynchronize(s));
+      TDM_CHECK_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(trace_path, "a")) {
+        fprintf(f, "# bwd Sq=%d Sk=%d d=%d events: MMA 0 top 1 pds_full seen 2 dV/S/dK issued 3 dq_free seen 4 dQ issued | compute 5 top 6 sdp_full seen 7 P stored 8 dq_full(i-1) seen 9 pds arrive | drain 10 dq_full seen 11 reduce issued\n",
+                a->Sq, a->Sk, a->d);
+        const long long t0 = host[0];
+        for (int g = 0; g < 32; ++g) {
+          if (!host[g * 16 + 1]) break;
+          fprintf(f, "%d", g);
+          for (int e = 0; e < 12; ++e) fprintf(f, " %lld", host[g * 16 + e] ? host[g * 16 + e] - t0 : -1);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+    }
   } else {
     const int smem = 4 * p.nd * CHUNK + 4 * CHUNK + 1024 + 256 + 1024;
     static int smem_set_w = 0;
