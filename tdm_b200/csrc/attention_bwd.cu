@@ -504,12 +504,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     else if (p.bias) bias_l2 = p.bias[(long)b * p.Sk + kv] * LOG2E;
     const long bh = (long)b * p.H + h;
     uint8_t* drow = sdSt + tid * 128;
+    // lse (warpgroup 0) / delta (warpgroup 1) of the tile's 128 queries: loaded one tile AHEAD into a register -- the
+    // global-memory round trip (~1000 clk) sat between two tiles on the loop's critical path (clock64 trace)
+    const float* stat_g = (wg == 0 ? p.lse : p.delta) + bh * p.Sq;
+    const float stat_oob = wg == 0 ? INFINITY : 0.f;
+    float stat_next = tid < p.Sq ? stat_g[tid] : stat_oob;
     for (int i = 0; i < n_q; ++i) {
-      const int q = i * 128 + tid;
       float* lse_s = sLse + (i & 1) * 128;
       float* del_s = sDelta + (i & 1) * 128;
-      if (wg == 0) lse_s[tid] = q < p.Sq ? p.lse[bh * p.Sq + q] * LOG2E : INFINITY;
-      else del_s[tid] = q < p.Sq ? p.delta[bh * p.Sq + q] : 0.f;
+      if (wg == 0) lse_s[tid] = stat_next * LOG2E;
+      else del_s[tid] = stat_next;
+      {
+        const int qn = (i + 1) * 128 + tid;
+        stat_next = (i + 1 < n_q && qn < p.Sq) ? stat_g[qn] : stat_oob;
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) BW_TRACE(i, 5);
       mbar_wait(sdp_full, i & 1);
