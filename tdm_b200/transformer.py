@@ -438,8 +438,8 @@ class Transformer2DModel(nn.Module):
         self._update_count += 1
 
     def _refresh_merged(self):
-        """W_eff16 = bf16(W32 + (alpha/r) * B A) for every adapted linear: one small tcgen05 GEMM each (K = r),
-        the fp32 master weight as the residual operand.  Redone only after the adapters changed."""
+        """W_eff16 = bf16(W32 + (alpha/r) * B A) for every adapted linear in ONE launch (csrc/lora_merge.cu).  Redone only
+        after the adapters changed."""
         key = (self._lflat._version, self._flat._version, self._update_count)
         if self._flat16_eff is not None and self._eff_key == key:
             return
@@ -447,7 +447,11 @@ class Transformer2DModel(nn.Module):
         if self._flat16_eff is None:
             self._flat16_eff = torch.empty_like(self._flat16)
             self._merged_structs = self._merge_table = None
-        self._flat16_eff.copy_(self._flat16)
+        if getattr(self, "_eff_base_version", None) != self._flat._version:
+            # everything that is NOT an adapted weight (biases, tables, embedders) is a plain copy of the bf16 arena; with a
+            # frozen base (the LoRA student) that copy is made once, not 1.2 GB per optimiser step
+            self._flat16_eff.copy_(self._flat16)
+            self._eff_base_version = self._flat._version
         if self._merge_table is None:
             self._build_merge_table()
         table, n_prob, n_tiles = self._merge_table
