@@ -19,6 +19,20 @@
 // and a two-stage K / V ring fit (192 KB).  TMA zero-fills columns >= d and rows >= S.
 // TMEM map: S_0 [0,128) S_1 [128,256) O_0 [256,256+16*ceil(d/16)) O_1 [384, ...); P_s (bf16 pairs) overwrites columns
 // [0,64) of S_s and is the A operand of P V straight from tensor memory.
+//
+// Measured alternatives that were NOT kept (B200, self-attention 8 x 16 x 1024 x 72; this form: 74-77 us, one-tile kernel 90):
+//   * whole 128-key row resident in registers (setmaxnreg 232 / 40): ptxas spills in every role, 117 us;
+//   * half a row resident, the other half re-read under the first half's exponentials (two tcgen05.ld rounds instead of
+//     four): 86-90 us -- register pressure costs more than the round trips save;
+//   * single pass with the stale maximum as the reference and a two-pass fallback (saves the maximum pass): 78.3 us;
+//   * one exponential in four as a degree-3 polynomial on the FMA pipe: 82.5 us (ncu: XU pipe 44 % busy, issue slots 36 %:
+//     neither is the limit -- 19 % of all warp samples sit in the softmax warps' wait for S, the rest is spread over
+//     long-scoreboard / fixed-latency stalls of ~700 instructions per warp and tile);
+//   * two warpgroups per stream, thread == half a row, maxima exchanged through shared memory (16 softmax warps, 96
+//     registers): 122 us.
+// What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
+// load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
+// ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us).
 #include <stdlib.h>
 #include "common.cuh"
 
