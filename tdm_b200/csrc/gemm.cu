@@ -140,13 +140,23 @@ __device__ __forceinline__ void gemm_epilogue_rows(const GemmParams& p, const CU
     tmem_ld32(taddr + c, acc);
     tmem_ld_wait();
     if (p.splits > 1) {  // accumulate-only split-K: partial sums meet in HBM
-      if (row_ok) {  // 16-byte vector reds: N % 8 == 0 and ld_out_f32 % 4 == 0 keep every group aligned and in range
-        float* o = p.out_f32 + (long)m * p.ld_out_f32 + n0 + c;
+      // The 32 x 32 fp32 chunk is staged like an fp32 output and ADDED by the TMA engine (cp.reduce.async.bulk.tensor):
+      // one bulk operation per chunk.  The first form issued red.global.add.v4.f32 per thread -- 32 rows = 32 memory
+      // transactions per instruction, 256 per chunk -- which clogs the SM's load/store queue that the mbarrier waits and
+      // tcgen05.ld of every warp share (found in the attention kernels, attention_fwd2.cu).  Rows >= M and columns >= N
+      // are clipped by the tensor map.
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          if (n0 + c + i < p.N)
-            red_add_v4(o + i, p.alpha * __uint_as_float(acc[i]), p.alpha * __uint_as_float(acc[i + 1]),
-                       p.alpha * __uint_as_float(acc[i + 2]), p.alpha * __uint_as_float(acc[i + 3]));
+      for (int g = 0; g < 8; ++g)
+        *reinterpret_cast<float4*>(stg_f + ((g ^ xf) << 4)) =
+            make_float4(p.alpha * __uint_as_float(acc[4 * g]), p.alpha * __uint_as_float(acc[4 * g + 1]),
+                        p.alpha * __uint_as_float(acc[4 * g + 2]), p.alpha * __uint_as_float(acc[4 * g + 3]));
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tmC32, stg, n0 + c, m0 + q * 32);
+        tma_store_commit();
       }
       continue;
     }
