@@ -32,6 +32,8 @@ struct AttnBwdParams {
   long dk_stride_b, dk_stride_s, dk_stride_h;
   bf16* dV;
   long dv_stride_b, dv_stride_s, dv_stride_h;
+  int dq_direct;     // one key tile per (batch, head) (cross-attention, Sk <= 128): every dQ tile is produced exactly once --
+                     // it is stored as bf16 straight into dQ (no zero fill, no fp32 accumulation, no cast kernel)
   long long* trace;  // TDM_B200_ATTN_TRACE: clock64 stamps of CTA (0,0,0), [query tile][16 events]
 };
 
@@ -61,8 +63,10 @@ __global__ void __launch_bounds__(256) attn_delta_rows_kernel(const bf16* __rest
     const float2 c0 = unpack_bf16(c.x), c1 = unpack_bf16(c.y), c2 = unpack_bf16(c.z), c3 = unpack_bf16(c.w);
     pw[u] = a0.x * c0.x + a0.y * c0.y + a1.x * c1.x + a1.y * c1.y + a2.x * c2.x + a2.y * c2.y + a3.x * c3.x + a3.y * c3.y;
   }
-  float4* z = reinterpret_cast<float4*>(dq_accum + row * (long)(H * d));
-  for (int i = lane; i < H * d / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dq_accum) {  // (null: the main kernel writes dQ directly, nothing to zero)
+    float4* z = reinterpret_cast<float4*>(dq_accum + row * (long)(H * d));
+    for (int i = lane; i < H * d / 4; i += 32) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   __syncwarp();
   for (int h = lane; h < H; h += 32) {
     float acc = 0.f;
@@ -91,8 +95,10 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
     acc += o0.x * g0.x + o0.y * g0.y + o1.x * g1.x + o1.y * g1.y + o2.x * g2.x + o2.y * g2.y + o3.x * g3.x + o3.y * g3.y;
   }
   delta[((long)b * H + h) * Sq + q] = acc;
-  float4* z = reinterpret_cast<float4*>(dq_accum + (((long)b * Sq + q) * H + h) * d);  // d % 8 == 0: 16-byte aligned
-  for (int c = 0; c < d / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (dq_accum) {
+    float4* z = reinterpret_cast<float4*>(dq_accum + (((long)b * Sq + q) * H + h) * d);  // d % 8 == 0: 16-byte aligned
+    for (int c = 0; c < d / 4; ++c) z[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 }
 
 __global__ void __launch_bounds__(192, 1)
@@ -326,7 +332,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const __grid_constant__ CUtensorMap tmdQ, const __grid_constant__ CUtensorMap tmdK,
-                const __grid_constant__ CUtensorMap tmdV, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmdV, const __grid_constant__ CUtensorMap tmdQ16,
+                const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // swizzled tiles need 1024-byte alignment
@@ -629,18 +636,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (i > 0) tma_store_wait_read();    // the previous tile's reduce has read the staging rows
       }
       __syncwarp();
+      if (p.dq_direct) {  // warp-uniform: bf16 rows, plain TMA store into the caller's dQ view
+        uint8_t* hrow = reinterpret_cast<uint8_t*>(stage) + lane * (p.d * 2);
 #pragma unroll
-      for (int c = 0; c < 20; ++c) {
-        if (4 * c < p.d)
-          *reinterpret_cast<float4*>(srow + 4 * c) =
-              make_float4(__uint_as_float(r[c >> 2][(c & 3) * 4]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 1]) * p.scale,
-                          __uint_as_float(r[c >> 2][(c & 3) * 4 + 2]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 3]) * p.scale);
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {  // rows >= Sq are clipped by the map
-        tma_reduce_add_3d(&tmdQ, stage, h * p.d, i * 128 + (warp & 3) * 32, b);
-        tma_store_commit();
+        for (int c = 0; c < 10; ++c) {
+          if (8 * c < p.d) {
+#define BW_Q(k_) (__uint_as_float(r[c >> 1][(c & 1) * 8 + (k_)]) * p.scale)
+            uint4 w;
+            w.x = pack_bf16(BW_Q(0), BW_Q(1));
+            w.y = pack_bf16(BW_Q(2), BW_Q(3));
+            w.z = pack_bf16(BW_Q(4), BW_Q(5));
+            w.w = pack_bf16(BW_Q(6), BW_Q(7));
+#undef BW_Q
+            *reinterpret_cast<uint4*>(hrow + 16 * c) = w;
+          }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {  // rows >= Sq are clipped by the map
+          tma_store_4d(&tmdQ16, stage, 0, i * 128 + (warp & 3) * 32, h, b);
+          tma_store_commit();
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 20; ++c) {
+          if (4 * c < p.d)
+            *reinterpret_cast<float4*>(srow + 4 * c) =
+                make_float4(__uint_as_float(r[c >> 2][(c & 3) * 4]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 1]) * p.scale,
+                            __uint_as_float(r[c >> 2][(c & 3) * 4 + 2]) * p.scale, __uint_as_float(r[c >> 2][(c & 3) * 4 + 3]) * p.scale);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {  // rows >= Sq are clipped by the map
+          tma_reduce_add_3d(&tmdQ, stage, h * p.d, i * 128 + (warp & 3) * 32, b);
+          tma_store_commit();
+        }
       }
       if (threadIdx.x == 256) BW_TRACE(i, 11);
     }
@@ -688,17 +718,21 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   if ((rc = make_head_map(&tmdO, a->dO, a->B, a->Sq, a->H, a->d, a->o_stride_b, a->o_stride_s, a->o_stride_h))) return rc;
   const long rows = (long)a->B * a->Sq;
   const int HD = a->H * a->d;
+  // one key tile per (batch, head) on the pipelined kernel: dQ is written directly (see AttnBwdParams::dq_direct)
+  const bool narrow = ((a->d + 15) / 16) * 16 <= 80 && (((long)a->H * a->d) % 4 == 0) && (a->d % 4 == 0);
+  const bool dq_direct = narrow && a->Sk <= 128;
+  float* dq_zero = dq_direct ? nullptr : a->dq_accum;
   if (a->o_stride_h == a->d && (size_t)(8 * a->H * a->d / 8) * 4 <= 48 * 1024) {
     ::tdm::count_launch();
     TDM_CHECK_CUDA(launch_pdl(attn_delta_rows_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), (size_t)(8 * (a->H * a->d / 8) * 4), s,
-                              (const bf16*)a->O, (const bf16*)a->dO, (long)a->o_stride_b, (long)a->o_stride_s, a->delta, a->dq_accum,
+                              (const bf16*)a->O, (const bf16*)a->dO, (long)a->o_stride_b, (long)a->o_stride_s, a->delta, dq_zero,
                               a->B, a->H, a->Sq, a->d));
   } else {
     const long total = rows * a->H;
     ::tdm::count_launch();
     TDM_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)0, s, (const bf16*)a->O,
                               (const bf16*)a->dO, (long)a->o_stride_b, (long)a->o_stride_s, (long)a->o_stride_h, a->delta,
-                              a->dq_accum, a->B, a->H, a->Sq, a->d));
+                              dq_zero, a->B, a->H, a->Sq, a->d));
   }
   AttnBwdParams p;
   p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.d = a->d;
@@ -709,12 +743,13 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
   p.dV = (bf16*)a->dV; p.dv_stride_b = a->dv_stride_b; p.dv_stride_s = a->dv_stride_s; p.dv_stride_h = a->dv_stride_h;
   dim3 grid((a->Sk + 127) / 128, a->H, a->B);
   p.nc = (a->d + 31) / 32;
-  if (p.dk16 * 16 <= 80 && (((long)a->H * a->d) % 4 == 0) && (a->d % 4 == 0)) {
+  p.dq_direct = dq_direct ? 1 : 0;
+  if (narrow) {
     if ((rc = make_head_map64(&tmQ, a->Q, a->B, a->Sq, a->H, a->d, a->q_stride_b, a->q_stride_s, a->q_stride_h))) return rc;
     if ((rc = make_head_map64(&tmK, a->K, a->B, a->Sk, a->H, a->d, a->k_stride_b, a->k_stride_s, a->k_stride_h))) return rc;
     if ((rc = make_head_map64(&tmV, a->V, a->B, a->Sk, a->H, a->d, a->v_stride_b, a->v_stride_s, a->v_stride_h))) return rc;
     if ((rc = make_head_map64(&tmdO, a->dO, a->B, a->Sq, a->H, a->d, a->o_stride_b, a->o_stride_s, a->o_stride_h))) return rc;
-    CUtensorMap tmdQ, tmdK, tmdV;
+    CUtensorMap tmdQ, tmdK, tmdV, tmdQ16;
     {  // fp32 accumulator [B, Sq, H*d]: one 32-row x d box per drain warp; bf16 dK / dV views [B, Sk, H, d]
       uint64_t dims[3] = {(uint64_t)HD, (uint64_t)a->Sq, (uint64_t)a->B};
       uint64_t strides[2] = {(uint64_t)HD * 4, (uint64_t)a->Sq * HD * 4};
@@ -726,6 +761,9 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
       if ((rc = make_tma_bf16(&tmdK, a->dK, 4, dims4, sk, box4, TMA_SWZ_NONE))) return rc;
       uint64_t sv[3] = {(uint64_t)a->dv_stride_s * 2, (uint64_t)a->dv_stride_h * 2, (uint64_t)a->dv_stride_b * 2};
       if ((rc = make_tma_bf16(&tmdV, a->dV, 4, dims4, sv, box4, TMA_SWZ_NONE))) return rc;
+      uint64_t dimsq[4] = {(uint64_t)a->d, (uint64_t)a->Sq, (uint64_t)a->H, (uint64_t)a->B};
+      uint64_t sq[3] = {(uint64_t)a->dq_stride_s * 2, (uint64_t)a->dq_stride_h * 2, (uint64_t)a->dq_stride_b * 2};
+      if ((rc = make_tma_bf16(&tmdQ16, a->dQ, 4, dimsq, sq, box4, TMA_SWZ_NONE))) return rc;
     }
     const int smem = 6 * p.nc * CH64 + 2 * CHUNK + 128 * a->d * 4 + 2048 + 256;
     static int smem_set = 0;
@@ -743,8 +781,8 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
       p.trace = trace_buf;
     }
     ::tdm::count_launch();
-    if (p.trace) TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
-    else TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, p));
+    if (p.trace) TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, tmdQ16, p));
+    else TDM_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, grid, dim3(BWD_THREADS), (size_t)smem, s, tmQ, tmK, tmV, tmdO, tmdQ, tmdK, tmdV, tmdQ16, p));
     if (p.trace) {
       static long long host[32 * 16];
       TDM_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -772,6 +810,7 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
     ::tdm::count_launch(); attn_bwd_wide_kernel<<<grid, 192, smem, s>>>(tmQ, tmK, tmV, tmdO, p);
   }
   TDM_CHECK_CUDA(cudaGetLastError());
+  if (dq_direct) return TDM_OK;
   // dQ scratch [B*Sq, H*d] fp32 -> bf16 dQ with the caller's strides (requires the [tokens, H*d] layout)
   const int nblk = num_sms() * 8;
   ::tdm::count_launch();
