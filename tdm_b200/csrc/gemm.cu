@@ -29,6 +29,14 @@ struct GemmParams {
   int seg_n, seg_k2;
   int seg_k, seg_m, seg_nb;  // stacked problems in one launch (single-CTA kernel): see TdmGemm
   int num_m_tiles, num_n_tiles;
+  // CTA-pair kernel, BN = 256, last column tile at most BN / 2 wide (N = 1152, 3456: most GEMMs of a DiT block):
+  //   narrow_last: that tile is computed with N = BN / 2 MMAs (half the tensor time and half the B traffic; the first form
+  //                issued full-width MMAs on zero-filled B rows, so a 128-column tail cost as much as a 256-column tile);
+  //   bal:         the narrow tiles are dealt to the pairs that would otherwise carry one tile more than the others.  Units
+  //                go round-robin to the pairs; positions [bal_a0, bal_a1) u [bal_b0, bal_b1) u [bal_c0, bal_c1) of the unit
+  //                sequence hold the narrow tiles: N = 1152 on 74 pairs = 128 full + 32 half tiles -> every pair <= 2.0
+  //                tile times instead of 3 (gemm_unit_tile, gemm_plan_balance).
+  int narrow_last, bal, bal_a0, bal_a1, bal_b0, bal_b1, bal_c0, bal_c1;
   int splits;        // split-K factor (>1 only in accumulate-only mode: partial sums are red.add'ed into out_f32)
   int stages;        // depth of the TMA<->MMA shared-memory ring (chosen on the host: what the epilogue leaves free)
   int epi_bytes;     // bytes of epilogue staging that follow the ring
@@ -115,6 +123,28 @@ __device__ __forceinline__ void gemm_epilogue_stage_vectors(const GemmParams& p,
     sg[n] = (gate_tile && ok) ? gate_tile[n0 + n] : 1.f;
   }
   epi_barrier();
+}
+
+// Unit (position in the round-robin sequence) -> tile coordinates.  Identity order (n fastest) unless p.bal.
+__device__ __forceinline__ void gemm_unit_tile(const GemmParams& p, int tile, int& mt, int& nt) {
+  const int nn = p.num_n_tiles;
+  if (!p.bal) {
+    mt = tile / nn;
+    nt = tile - mt * nn;
+    return;
+  }
+  auto below = [](int u, int lo, int hi) { return u <= lo ? 0 : (u < hi ? u - lo : hi - lo); };  // positions of [lo, hi) before u
+  const int narrow_before = below(tile, p.bal_a0, p.bal_a1) + below(tile, p.bal_b0, p.bal_b1) + below(tile, p.bal_c0, p.bal_c1);
+  const bool is_narrow = (tile >= p.bal_a0 && tile < p.bal_a1) || (tile >= p.bal_b0 && tile < p.bal_b1) ||
+                         (tile >= p.bal_c0 && tile < p.bal_c1);
+  if (is_narrow) {
+    mt = narrow_before;
+    nt = nn - 1;
+  } else {
+    const int f = tile - narrow_before;
+    mt = f / (nn - 1);
+    nt = f - mt * (nn - 1);
+  }
 }
 
 // Fused epilogue of one 128-row accumulator quarter: thread == accumulator row (tcgen05.ld 32x32b), so the 32 values
@@ -507,10 +537,9 @@ __device__ __forceinline__ void gemm_epilogue_warp_loop(const GemmParams& p, con
   const int ch = ew >> 2;  // even / odd 32-column chunks of the tile
   const int feat_slot = p.epi_feat_slot;
   float bias_r[NCH], gate_r[NCH];
-  // tile coordinates advance incrementally (FAST kernels never split K: unit == tile): no division in the tile loop
-  const int nn = p.num_n_tiles;
-  const int step_m = unit_step / nn, step_n = unit_step - step_m * nn;
-  int mt = unit0 / nn, nt = unit0 - mt * nn;
+  // FAST kernels never split K: unit == tile.  One gemm_unit_tile per tile (two integer divisions every ~8 us).
+  int mt, nt;
+  gemm_unit_tile(p, unit0 < num_units ? unit0 : 0, mt, nt);
   auto fetch_vec = [&](int mt_, int nt_) {
     const int m0_ = mt_ * (PAIR ? 2 * BM : BM) + rank * BM, n0_ = nt_ * BN;
     const float* gate_tile = nullptr;
@@ -539,13 +568,10 @@ __device__ __forceinline__ void gemm_epilogue_warp_loop(const GemmParams& p, con
       asm volatile("st.shared.f32 [%0], %1;" ::"r"(vec + k * 256 + 128 + lane * 4), "f"(gate_r[k]) : "memory");
     }
     __syncwarp();
-    mt += step_m;
-    nt += step_n;
-    if (nt >= nn) {
-      nt -= nn;
-      ++mt;
+    if (unit + unit_step < num_units) {
+      gemm_unit_tile(p, unit + unit_step, mt, nt);
+      fetch_vec(mt, nt);  // the next tile's rows travel during this tile
     }
-    if (unit + unit_step < num_units) fetch_vec(mt, nt);  // the next tile's rows travel during this tile
     const uint32_t taddr = tmem_base + as * acc_stride + (uint32_t(q * 32) << 16);
 #ifndef TDM_DBG_NOEPI
 #define TDM_EPI_CASE(F) \
@@ -872,9 +898,14 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t phase = 0;
       for (int unit = pair; unit < num_units; unit += npairs) {
         const int tile = unit / p.splits, sp = unit - tile * p.splits;
-        const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
-        const int nh = n0 + (int)rank * (BN / 2);  // this CTA's half of the B tile
+        int mt, nt;
+        gemm_unit_tile(p, tile, mt, nt);
+        const int m0 = mt * (2 * BM) + (int)rank * BM;
+        const int n0 = nt * BN;
+        // this CTA's half of the B tile; a narrow last tile is an N = BN / 2 MMA whose halves are BN / 4 rows each (the box
+        // still brings BN / 2 rows: the MMA reads the first BN / 4 of them)
+        const bool narrow = p.narrow_last && nt == p.num_n_tiles - 1;
+        const int nh = n0 + (int)rank * (narrow ? BN / 4 : BN / 2);
         const int seg = p.seg_n > 0 ? n0 / p.seg_n : 0;
         const int kb0 = (int)((long)sp * nk / p.splits), kb1 = (int)((long)(sp + 1) * nk / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -929,11 +960,18 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t idesc_narrow = make_idesc_bf16(2 * BM, BN / 2, p.a_mn, p.b_mn);
       for (int unit = pair; unit < num_units; unit += npairs, ++it) {
         const int tile = unit / p.splits, sp = unit - tile * p.splits;
         const int kb0 = (int)((long)sp * nk / p.splits), kb1 = (int)((long)(sp + 1) * nk / p.splits);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        uint32_t idesc_u = idesc;
+        if (p.narrow_last) {
+          int mt, nt;
+          gemm_unit_tile(p, tile, mt, nt);
+          if (nt == p.num_n_tiles - 1) idesc_u = idesc_narrow;
+        }
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * Cfg::ACC_STRIDE;
@@ -946,7 +984,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
 #ifndef TDM_DBG_NOMMA
-              umma_bf16_2cta(tmem_d, da + uint64_t(k * a_kstep), db + uint64_t(k * b_kstep), idesc, (kb > kb0) || (k != 0));
+              umma_bf16_2cta(tmem_d, da + uint64_t(k * a_kstep), db + uint64_t(k * b_kstep), idesc_u, (kb > kb0) || (k != 0));
 #endif
             }
             umma_commit_2cta(&empty_bar[stage]);  // frees the stage in BOTH CTAs when these MMAs retire
@@ -977,8 +1015,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int tile = unit / p.splits;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
-        const int m0 = (tile / p.num_n_tiles) * (2 * BM) + (int)rank * BM;
-        const int n0 = (tile % p.num_n_tiles) * BN;
+        int mt, nt;
+        gemm_unit_tile(p, tile, mt, nt);
+        const int m0 = mt * (2 * BM) + (int)rank * BM;
+        const int n0 = nt * BN;
         gemm_epilogue_stage_vectors<BN>(p, epi_vec, as, m0, n0, ew * 32 + lane);
         const uint32_t taddr = tmem_base + as * Cfg::ACC_STRIDE + (uint32_t(q * 32) << 16);
         mbar_wait(&tfull_bar[as], aphase);
@@ -1054,6 +1094,27 @@ static int gemm_plan_splits(const TdmGemm* g, int tiles0, int slots) {
   return best;
 }
 
+// Positions of the narrow (half-cost) tiles in the round-robin unit sequence of `slots` pairs: the last round's positions
+// (pairs 0 .. L-1 carry one unit more than the others), then the same pairs' positions one round earlier (two halves ~ one
+// full tile), the rest on the highest pairs of that round.  Left off (identity order) when the pattern does not fit.
+static void gemm_plan_balance(GemmParams* p, int slots) {
+  const int T = p->num_m_tiles * p->num_n_tiles, H = p->num_m_tiles;
+  const int P = T < slots ? T : slots;
+  const int R = (T + P - 1) / P;
+  if (R < 2) return;
+  const int L = T - (R - 1) * P;  // units of the last round
+  if (L == P) return;             // full last round: nothing to balance
+  const int c = H < L ? H : L;
+  const int h1 = H - c;
+  const int a = h1 < L ? h1 : L;
+  const int h2 = h1 - a;
+  if (h2 > P - a) return;
+  p->bal = 1;
+  p->bal_a0 = (R - 2) * P; p->bal_a1 = p->bal_a0 + a;
+  p->bal_b1 = (R - 1) * P; p->bal_b0 = p->bal_b1 - h2;
+  p->bal_c0 = (R - 1) * P; p->bal_c1 = p->bal_c0 + c;
+}
+
 template <int BN, bool PAIR>
 static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   constexpr int STAGE_BYTES = PAIR ? Gemm2Cfg<BN>::STAGE_BYTES : GemmCfg<BN>::STAGE_BYTES;
@@ -1108,6 +1169,16 @@ static int launch_gemm(const TdmGemm* g, cudaStream_t stream) {
   if (g->split_k > 1 && !gemm_acc_only(g))
     return set_error(TDM_ERR_INVALID, "tdm_gemm_bf16: split_k needs an accumulate-only epilogue (res == out_f32)");
   p.splits = gemm_plan_splits(g, p.num_m_tiles * p.num_n_tiles, PAIR ? num_sms() / 2 : num_sms());
+  p.narrow_last = p.bal = 0;
+  p.bal_a0 = p.bal_a1 = p.bal_b0 = p.bal_b1 = p.bal_c0 = p.bal_c1 = 0;
+  if constexpr (PAIR && BN == 256) {
+    const bool no_bal = getenv("TDM_B200_GEMM_BALANCE") && atoi(getenv("TDM_B200_GEMM_BALANCE")) == 0;  // A/B timing
+    const int tail = g->N - (p.num_n_tiles - 1) * BN;  // width of the last column tile
+    if (!no_bal && p.splits == 1 && p.num_n_tiles >= 2 && tail <= BN / 2 && g->seg_n == 0 && g->seg_k == 0 && g->seg_m == 0) {
+      p.narrow_last = 1;
+      gemm_plan_balance(&p, num_sms() / 2);
+    }
+  }
 
   // Epilogue flavour and shared-memory plan.  The streaming (FAST) epilogue moves every epilogue tensor by TMA; the
   // generic one keeps the rare features: split-K reductions, the row-modulo residual (pos_embed), the unrounded

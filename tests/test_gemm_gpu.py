@@ -274,3 +274,33 @@ def test_lora_merge_kernel_against_torch():
         assert torch.isfinite(weff.float()).all()
         err = (weff.float() - ref).abs()
         assert (err <= ref.abs() * 2.0 ** -8 + 1e-6).all(), err.max().item()
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(8192, 1152, 256, False), (8192, 1152, 256, True), (8192, 3456, 128, False),
+                                        (4096, 640, 192, True), (2304, 1152, 320, False), (19200, 384, 128, False)])
+def test_gemm_pair_narrow_tail_and_balanced_order(M, N, K, b_mn, monkeypatch):
+    """CTA-pair kernel, 256-column tiles, last column tile <= 128 columns wide: that tile runs N = 128 MMAs and the unit
+    order deals the narrow tiles to the pairs with one unit more (gemm_plan_balance).  Same values as the identity order
+    with full-width MMAs (TDM_B200_GEMM_BALANCE=0), bit for bit, with a residual + gate + two-output epilogue, and within
+    bf16 tolerance of the fp32 product."""
+    from tdm_b200 import ops
+    a = _mk((M, K), seed=31)
+    w = _mk((K, N) if b_mn else (N, K), 0.1, seed=32)
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    rows_per_gate = 128
+    gate = torch.randn((M + rows_per_gate - 1) // rows_per_gate, N, device="cuda")
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TDM_B200_GEMM_BALANCE", flag)
+        o32 = torch.full((M, N), float("nan"), device="cuda")
+        o16 = torch.full((M, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, w, b_mn_major=b_mn, bias=bias, gate=gate, rows_per_gate=rows_per_gate, res=res, out_f32=o32, out_bf16=o16,
+                 tile_n=256, cta_pair=2)
+        torch.cuda.synchronize()
+        outs.append((o32, o16))
+    wt = w.float() if b_mn else w.float().t()
+    ref = (a.float() @ wt + bias) * gate.repeat_interleave(rows_per_gate, 0)[:M] + res
+    assert torch.isfinite(outs[0][0]).all()
+    assert (outs[0][0] - ref).abs().max().item() < 2e-2 * ref.abs().max().item()
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
