@@ -23,6 +23,7 @@ constexpr int CH64 = 128 * 64;  // one [128 rows x 32 bf16] chunk, 64-byte swizz
 struct AttnBwdParams {
   int B, H, Sq, Sk, d, nd, dk16;
   int nc;  // ceil(d / 32): chunks of the 64-byte-swizzled tiles (attn_bwd_kernel)
+  int dq_stage_bytes;  // attn_bwd_kernel: bytes of the dQ staging area (column passes, or the bf16 tile of the direct path)
   float scale, scale_log2;
   const float* bias;   // [B, Sk] or null
   const float* lse;    // [B, H, Sq]
@@ -340,22 +341,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tile_bytes = p.nc * CH64;
   uint8_t* sK = smem;
   uint8_t* sV = sK + tile_bytes;
-  uint8_t* sQ = sV + tile_bytes;          // 2 stages
-  uint8_t* sdO = sQ + 2 * tile_bytes;     // 2 stages
+  uint8_t* sQ = sV + tile_bytes;          // 2 stages: Q(i) is held until dK(i); the reload (~2000 clk) is needed at S^T(i+2)
+  uint8_t* sdO = sQ + 2 * tile_bytes;     // 2 stages with their own barriers: dO(i) is released right behind dV(i), so the
+                                          // reload is back for dP^T(i+2), which is issued a phase earlier than S^T(i+2)
   uint8_t* sdSt = sdO + 2 * tile_bytes;   // [128 keys x 128 queries] bf16, 2 chunks of 64 columns, 128-byte swizzle
-  float* sdQ = reinterpret_cast<float*>(sdSt + 2 * CHUNK);   // [128 queries][d] fp32 staging of the dQ tile
-  float* sLse = sdQ + 128 * p.d;                             // 2 x 128 (log2 units)
+  float* sdQ = reinterpret_cast<float*>(sdSt + 2 * CHUNK);   // [128 queries][d] fp32 staging of the dQ tile (bf16 on the direct path)
+  float* sLse = sdQ + p.dq_stage_bytes / 4;                  // 2 x 128 (log2 units)
   float* sDelta = sLse + 256;                                 // 2 x 128
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* kv_full = bars;        // 1
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;   // S^T and dP^T of tile i complete
-  uint64_t* s_free = bars + 6;     // 128: compute warps hold S^T/dP^T of tile i in registers
-  uint64_t* pds_full = bars + 7;   // 128: P^T (TMEM) and dS^T (smem) of tile i written
-  uint64_t* dq_full = bars + 8;    // all MMAs of tile i complete (dQ ready, dS^T smem / Q / dO free)
-  uint64_t* dq_free = bars + 9;    // 128: dQ of tile i drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* q_full = bars + 1;     // [2] (+1 spare)
+  uint64_t* q_empty = bars + 4;    // [2] (+1 spare)
+  uint64_t* do_full = bars + 7;    // [2]
+  uint64_t* do_empty = bars + 9;   // [2]
+  uint64_t* st_full = bars + 11;   // S^T of tile i complete
+  uint64_t* dp_free = bars + 12;   // 8: compute warps hold dP^T of tile i in registers (its region takes S^T of tile i+1)
+  uint64_t* ds_full = bars + 13;   // 8: dS^T (smem) of tile i written
+  uint64_t* dq_full = bars + 14;   // all MMAs of tile i complete (dQ ready, dS^T smem free)
+  uint64_t* dq_free = bars + 15;   // 4: dQ of tile i drained
+  uint64_t* dpt_full = bars + 16;  // dP^T of tile i complete
+  uint64_t* p_full = bars + 17;    // 8: P^T of tile i written to tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -364,13 +370,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
     }
-    mbar_init(sdp_full, 1);
-    mbar_init(s_free, 8);    // one elected arrival per compute warp (per-thread arrivals serialise on the barrier word)
-    mbar_init(pds_full, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&do_full[i], 1);
+      mbar_init(&do_empty[i], 1);
+    }
+    mbar_init(st_full, 1);
+    mbar_init(dpt_full, 1);
+    mbar_init(dp_free, 8);   // one elected arrival per compute warp (per-thread arrivals serialise on the barrier word)
+    mbar_init(p_full, 8);
+    mbar_init(ds_full, 8);
     mbar_init(dq_full, 1);
     mbar_init(dq_free, 4);
     fence_barrier_init();
@@ -380,8 +392,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tm_St = tmem_base, tm_dPt = tmem_base + 128, tm_dV = tmem_base + 256, tm_dK = tmem_base + 336,
-                 tm_dQ = tmem_base + 416;
+  // Two 128-column regions R0 / R1 swap roles every tile: S^T(i) / P^T(i) live in R[i & 1], dP^T(i) in R[(i + 1) & 1].
+  const uint32_t tm_R = tmem_base, tm_dV = tmem_base + 256, tm_dK = tmem_base + 336, tm_dQ = tmem_base + 416;
   pdl_sync();
 
   if (warp == 12) {
@@ -395,13 +407,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tma_load_4d(sV + c * CH64, &tmV, kv_full, c * 32, k0, h, b);
       }
       for (int i = 0; i < n_q; ++i) {
-        const int st = i & 1;
-        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&qdo_full[st], 2 * tile_bytes);
-        for (int c = 0; c < p.nc; ++c) {
-          tma_load_4d(sQ + st * tile_bytes + c * CH64, &tmQ, &qdo_full[st], c * 32, i * 128, h, b);
-          tma_load_4d(sdO + st * tile_bytes + c * CH64, &tmdO, &qdo_full[st], c * 32, i * 128, h, b);
-        }
+        const int sd = i & 1, sq = i & 1;
+        const uint32_t qph = (i >> 1) & 1;
+        mbar_wait(&do_empty[sd], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&do_full[sd], tile_bytes);
+        for (int c = 0; c < p.nc; ++c) tma_load_4d(sdO + sd * tile_bytes + c * CH64, &tmdO, &do_full[sd], c * 32, i * 128, h, b);
+        mbar_wait(&q_empty[sq], qph ^ 1);
+        mbar_arrive_expect_tx(&q_full[sq], tile_bytes);
+        for (int c = 0; c < p.nc; ++c) tma_load_4d(sQ + sq * tile_bytes + c * CH64, &tmQ, &q_full[sq], c * 32, i * 128, h, b);
       }
     }
   } else if (warp == 13) {
@@ -423,66 +436,91 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint64_t ddS_mn = make_sdesc_sw128(smem_u32(sdSt), CHUNK, 1024);
     const uint32_t stage_step = uint32_t(tile_bytes) >> 4;
     const int dk16 = p.dk16;
-    auto issue_st = [&](int i) {  // caller holds the election
-      const uint64_t qd = dQ_k0 + uint64_t((i & 1) * stage_step);
+    auto issue_st = [&](int i, int qs) {  // caller holds the election; qs = Q stage of tile i
+      const uint64_t qd = dQ_k0 + uint64_t(qs * stage_step);
+      const uint32_t dst = tm_R + (i & 1) * 128;
 #pragma unroll
       for (int k = 0; k < 5; ++k)
         if (k < dk16) {
           const uint32_t off = ((k >> 1) * CH64 + (k & 1) * 32) >> 4;
-          umma_bf16(tm_St, dK_k + off, qd + off, id_kk, k != 0);
+          umma_bf16(dst, dK_k + off, qd + off, id_kk, k != 0);
         }
     };
     auto issue_dpt = [&](int i) {
       const uint64_t od = ddO_k0 + uint64_t((i & 1) * stage_step);
+      const uint32_t dst = tm_R + ((i + 1) & 1) * 128;
 #pragma unroll
       for (int k = 0; k < 5; ++k)
         if (k < dk16) {
           const uint32_t off = ((k >> 1) * CH64 + (k & 1) * 32) >> 4;
-          umma_bf16(tm_dPt, dV_k + off, od + off, id_kk, k != 0);
+          umma_bf16(dst, dV_k + off, od + off, id_kk, k != 0);
         }
     };
+    // Per tile the compute warps run two phases -- A: P^T from S^T (exponentials), B: dS^T from dP^T -- and this warp
+    // answers three events in the order they occur:
+    //   P^T(i) written        -> dV(i), then dP^T(i+1) into the region that held S^T(i) / P^T(i) (in order behind dV(i))
+    //   dP^T(i) in registers  -> S^T(i+1) into the region that held dP^T(i)
+    //   dS^T(i) written       -> dK(i), dQ(i)
+    // so S^T(i+1) is complete before the compute warps finish tile i and dP^T(i+1) long before they need it: the tensor
+    // work of a tile runs under the compute phases instead of between them (the first form produced S^T(i+1) and
+    // dP^T(i+1) only after P^T / dS^T of tile i: compute 2560 clk + tensor / hand-off 1350 clk per tile, serial).
     mbar_wait(kv_full, 0);
-    mbar_wait(&qdo_full[0], 0);
+    mbar_wait(&q_full[0], 0);
+    mbar_wait(&do_full[0], 0);
     tc_fence_after();
     if (elect_one()) {
-      issue_st(0);
+      issue_st(0, 0);
+      umma_commit(st_full);
       issue_dpt(0);
-      umma_commit(sdp_full);
+      umma_commit(dpt_full);
     }
     __syncwarp();
     for (int i = 0; i < n_q; ++i) {
-      const int st = i & 1;
-      if (i + 1 < n_q) {
-        mbar_wait(&qdo_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
-        mbar_wait(s_free, i & 1);  // the dP^T columns are in registers now
-        tc_fence_after();
-        if (elect_one()) issue_dpt(i + 1);
-        __syncwarp();
-      }
+      const int sd = i & 1, qs = i & 1;
+      const bool more = i + 1 < n_q;
+      const int qs1 = (i + 1) & 1;
+      const uint32_t qph1 = ((i + 1) >> 1) & 1;
       if (lane == 0) BW_TRACE(i, 0);
-      mbar_wait(pds_full, i & 1);
+      mbar_wait(p_full, i & 1);
+      if (more) mbar_wait(&do_full[(i + 1) & 1], ((i + 1) >> 1) & 1);
       tc_fence_after();
       if (lane == 0) BW_TRACE(i, 1);
       if (elect_one()) {
-        const uint64_t od_mn = ddO_mn0 + uint64_t(st * stage_step), qd_mn = dQ_mn0 + uint64_t(st * stage_step);
+        const uint64_t od_mn = ddO_mn0 + uint64_t(sd * stage_step);
+        const uint32_t pt = tm_R + (i & 1) * 128;
 #pragma unroll
         for (int k = 0; k < 8; ++k)  // dV += P^T dO : contraction over the 128 queries, A from tensor memory
-          umma_bf16_ts(tm_dV, tm_St + (k >> 2) * 64 + (k & 3) * 8, od_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
-        if (i + 1 < n_q) {
-          issue_st(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
-          umma_commit(sdp_full);
+          umma_bf16_ts(tm_dV, pt + (k >> 2) * 64 + (k & 3) * 8, od_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
+        umma_commit(&do_empty[sd]);  // dV(i) is the last reader of dO(i)
+        if (more) {
+          issue_dpt(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
+          umma_commit(dpt_full);
         }
+      }
+      __syncwarp();
+      if (more) {
+        mbar_wait(dp_free, i & 1);
+        mbar_wait(&q_full[qs1], qph1);
+        tc_fence_after();
+        if (elect_one()) {
+          issue_st(i + 1, qs1);
+          umma_commit(st_full);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) BW_TRACE(i, 2);
+      mbar_wait(ds_full, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qd_mn = dQ_mn0 + uint64_t(qs * stage_step);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // dK += dS^T Q
           const uint32_t offA = ((k >> 2) * CHUNK + (k & 3) * 32) >> 4;
           umma_bf16(tm_dK, ddS_k + offA, qd_mn + uint64_t(k * (1024 >> 4)), id_kmn, (i | k) != 0);
         }
-        // dK(i) is the last reader of Q(i), dV(i) of dO(i): the stage is released HERE, not behind dQ(i) -- the reload
-        // (tile i+2) has a ~2500 clk round trip and the loop was waiting for it (clock64 trace, profiles/)
-        umma_commit(&qdo_empty[st]);
+        umma_commit(&q_empty[qs]);  // dK(i) is the last reader of Q(i)
       }
       __syncwarp();
-      if (lane == 0) BW_TRACE(i, 2);
       if (i > 0) {
         mbar_wait(dq_free, (i - 1) & 1);
         tc_fence_after();
@@ -527,42 +565,63 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 0) BW_TRACE(i, 5);
-      mbar_wait(sdp_full, i & 1);
+      const uint32_t tm_S = tm_R + (i & 1) * 128 + lane_off, tm_dP = tm_R + ((i + 1) & 1) * 128 + lane_off;
+      // ---- phase A: P^T = exp2(S^T * scale + bias - lse) -> packed bf16 into this warpgroup's OWN half of the S^T columns
+      //      ([0,32) / [64,96): never passes the columns it still has to read, never touches the other warpgroup's) ----
+      mbar_wait(st_full, i & 1);
       tc_fence_after();
       if (threadIdx.x == 0) BW_TRACE(i, 6);
-#pragma unroll 1
+      float pf[64];
+#pragma unroll
       for (int cc = 0; cc < 2; ++cc) {
         const int c = wg * 2 + cc;
-        uint32_t rs[32], rp[32];
-        tmem_ld32(tm_St + lane_off + c * 32, rs);
-        tmem_ld32(tm_dPt + lane_off + c * 32, rp);
+        uint32_t rs[32];
+        tmem_ld32(tm_S + c * 32, rs);
         tmem_ld_wait();
-        if (cc == 1) {  // everything this thread needs of the tile is in registers: dP^T may be overwritten
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);
-        }
-        uint32_t pk[16], dk[16];
+        uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const int x = c * 32 + 2 * j;
-          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + x);
-          const float4 d4 = *reinterpret_cast<const float4*>(del_s + x);
+          const float4 l4 = *reinterpret_cast<const float4*>(lse_s + c * 32 + 2 * j);
           const float p0 = ex2_fast(fmaf(__uint_as_float(rs[2 * j]), p.scale_log2, bias_l2) - l4.x);
           const float p1 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 1]), p.scale_log2, bias_l2) - l4.y);
           const float p2 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 2]), p.scale_log2, bias_l2) - l4.z);
           const float p3 = ex2_fast(fmaf(__uint_as_float(rs[2 * j + 3]), p.scale_log2, bias_l2) - l4.w);
+          pf[cc * 32 + 2 * j] = p0; pf[cc * 32 + 2 * j + 1] = p1; pf[cc * 32 + 2 * j + 2] = p2; pf[cc * 32 + 2 * j + 3] = p3;
           pk[j] = pack_bf16(p0, p1);
           pk[j + 1] = pack_bf16(p2, p3);
-          dk[j] = pack_bf16(p0 * (__uint_as_float(rp[2 * j]) - d4.x), p1 * (__uint_as_float(rp[2 * j + 1]) - d4.y));
-          dk[j + 1] = pack_bf16(p2 * (__uint_as_float(rp[2 * j + 2]) - d4.z), p3 * (__uint_as_float(rp[2 * j + 3]) - d4.w));
         }
-        // P^T packed into this warpgroup's OWN half of the S^T columns ([0,32) / [64,96)): never passes the columns
-        // it still has to read, and never touches the other warpgroup's
-        tmem_st16(tm_St + lane_off + wg * 64 + cc * 16, pk);
-        if (threadIdx.x == 0 && cc == 0) BW_TRACE(i, 7);
-        if (cc == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
+        tmem_st16(tm_S + wg * 64 + cc * 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      if (threadIdx.x == 0) BW_TRACE(i, 7);
+      // ---- phase B: dS^T = P^T o (dP^T - delta) -> shared memory (K-major for dK, MN-major for dQ) ----
+      mbar_wait(dpt_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = wg * 2 + cc;
+        uint32_t rp[32];
+        tmem_ld32(tm_dP + c * 32, rp);
+        tmem_ld_wait();
+        if (cc == 1) {  // dP^T(i) is in registers: its region may take S^T(i+1)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dp_free);
+        }
+        uint32_t dk[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float4 d4 = *reinterpret_cast<const float4*>(del_s + c * 32 + 2 * j);
+          dk[j] = pack_bf16(pf[cc * 32 + 2 * j] * (__uint_as_float(rp[2 * j]) - d4.x),
+                            pf[cc * 32 + 2 * j + 1] * (__uint_as_float(rp[2 * j + 1]) - d4.y));
+          dk[j + 1] = pack_bf16(pf[cc * 32 + 2 * j + 2] * (__uint_as_float(rp[2 * j + 2]) - d4.z),
+                                pf[cc * 32 + 2 * j + 3] * (__uint_as_float(rp[2 * j + 3]) - d4.w));
+        }
         if (threadIdx.x == 0 && cc == 0) BW_TRACE(i, 8);
+        if (cc == 0 && i > 0) mbar_wait(dq_full, (i - 1) & 1);  // dK/dQ of the previous tile no longer read dS^T
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
           const int U = c * 4 + u4;
@@ -570,11 +629,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           *reinterpret_cast<uint4*>(drow + off) = make_uint4(dk[u4 * 4], dk[u4 * 4 + 1], dk[u4 * 4 + 2], dk[u4 * 4 + 3]);
         }
       }
-      tmem_st_wait();
       fence_async_smem();
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(ds_full);
       if (threadIdx.x == 0) BW_TRACE(i, 9);
     }
     // epilogue: warps 0-3 write dV, warps 4-7 write dK of this key tile (thread == key row)
@@ -631,13 +688,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(dq_free);                // dQ is in registers: the next tile's dQ may be issued
-        if (i > 0) tma_store_wait_read();    // the previous tile's reduce has read the staging rows
-      }
-      __syncwarp();
-      if (p.dq_direct) {  // warp-uniform: bf16 rows, plain TMA store into the caller's dQ view
-        uint8_t* hrow = reinterpret_cast<uint8_t*>(stage) + lane * (p.d * 2);
+      if (lane == 0) mbar_arrive(dq_free);  // dQ is in registers: the next tile's dQ may be issued
+      if (p.dq_direct) {  // warp-uniform: bf16 rows, one plain TMA store into the caller's dQ view
+        if (lane == 0 && i > 0) tma_store_wait_read();
+        __syncwarp();
+        uint8_t* hrow = reinterpret_cast<uint8_t*>(sdQ) + (warp & 3) * (32 * p.d * 2) + lane * (p.d * 2);
 #pragma unroll
         for (int c = 0; c < 10; ++c) {
           if (8 * c < p.d) {
@@ -654,10 +709,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {  // rows >= Sq are clipped by the map
-          tma_store_4d(&tmdQ16, stage, 0, i * 128 + (warp & 3) * 32, h, b);
+          tma_store_4d(&tmdQ16, reinterpret_cast<uint8_t*>(sdQ) + (warp & 3) * (32 * p.d * 2), 0, i * 128 + (warp & 3) * 32, h, b);
           tma_store_commit();
         }
       } else {
+        if (lane == 0 && i > 0) tma_store_wait_read();  // the previous tile's reduce has read the staging rows
+        __syncwarp();
 #pragma unroll
         for (int c = 0; c < 20; ++c) {
           if (4 * c < p.d)
@@ -765,7 +822,8 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
       uint64_t sq[3] = {(uint64_t)a->dq_stride_s * 2, (uint64_t)a->dq_stride_h * 2, (uint64_t)a->dq_stride_b * 2};
       if ((rc = make_tma_bf16(&tmdQ16, a->dQ, 4, dimsq, sq, box4, TMA_SWZ_NONE))) return rc;
     }
-    const int smem = 6 * p.nc * CH64 + 2 * CHUNK + 128 * a->d * 4 + 2048 + 256;
+    p.dq_stage_bytes = 128 * a->d * 4;
+    const int smem = 6 * p.nc * CH64 + 2 * CHUNK + p.dq_stage_bytes + 2048 + 256;
     static int smem_set = 0;
     if (smem > smem_set) {
       TDM_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -788,7 +846,7 @@ extern "C" int tdm_attn_bwd(const TdmAttn* a, void* stream) {
       TDM_CHECK_CUDA(cudaStreamSynchronize(s));
       TDM_CHECK_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
       if (FILE* f = fopen(trace_path, "a")) {
-        fprintf(f, "# bwd Sq=%d Sk=%d d=%d events: MMA 0 top 1 pds_full seen 2 dV/S/dK issued 3 dq_free seen 4 dQ issued | compute 5 top 6 sdp_full seen 7 P stored 8 dq_full(i-1) seen 9 pds arrive | drain 10 dq_full seen 11 reduce issued\n",
+        fprintf(f, "# bwd Sq=%d Sk=%d d=%d events: MMA 0 top 1 p_full seen 2 S^T(i+1) issued 3 dq_free seen 4 dQ issued | compute 5 top 6 st_full seen 7 P^T arrive 8 first dS chunk ready 9 ds arrive | drain 10 dq_full seen 11 reduce issued\n",
                 a->Sq, a->Sk, a->d);
         const long long t0 = host[0];
         for (int g = 0; g < 32; ++g) {
