@@ -359,9 +359,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* ds_full = bars + 13;   // 8: dS^T (smem) of tile i written
   uint64_t* dq_full = bars + 14;   // all MMAs of tile i complete (dQ ready, dS^T smem free)
   uint64_t* dq_free = bars + 15;   // 4: dQ of tile i drained
-  uint64_t* dpt_full = bars + 16;  // dP^T of tile i complete
-  uint64_t* p_full = bars + 17;    // 8: P^T of tile i written to tensor memory
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  // dP^T of tile i complete: ONE BARRIER PER TILE PARITY.  dP^T(i+1) is issued as soon as P^T(i) is written, i.e. possibly
+  // before a compute warp has started to wait for dP^T(i): on a single barrier the awaited parity would flip back and the
+  // wait never return (seen as a hang once in ~100 000 launches; same rule as attention_fwd.cu's p_full).
+  uint64_t* dpt_full = bars + 16;  // [2]
+  uint64_t* p_full = bars + 18;    // 8: P^T of tile i written to tensor memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -379,7 +382,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&do_empty[i], 1);
     }
     mbar_init(st_full, 1);
-    mbar_init(dpt_full, 1);
+    mbar_init(&dpt_full[0], 1);
+    mbar_init(&dpt_full[1], 1);
     mbar_init(dp_free, 8);   // one elected arrival per compute warp (per-thread arrivals serialise on the barrier word)
     mbar_init(p_full, 8);
     mbar_init(ds_full, 8);
@@ -472,7 +476,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       issue_st(0, 0);
       umma_commit(st_full);
       issue_dpt(0);
-      umma_commit(dpt_full);
+      umma_commit(&dpt_full[0]);
     }
     __syncwarp();
     for (int i = 0; i < n_q; ++i) {
@@ -494,7 +498,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         umma_commit(&do_empty[sd]);  // dV(i) is the last reader of dO(i)
         if (more) {
           issue_dpt(i + 1);  // overwrites P^T(i): ordered after dV(i) by the in-order tensor pipe
-          umma_commit(dpt_full);
+          umma_commit(&dpt_full[(i + 1) & 1]);
         }
       }
       __syncwarp();
@@ -598,7 +602,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (lane == 0) mbar_arrive(p_full);
       if (threadIdx.x == 0) BW_TRACE(i, 7);
       // ---- phase B: dS^T = P^T o (dP^T - delta) -> shared memory (K-major for dK, MN-major for dQ) ----
-      mbar_wait(dpt_full, i & 1);
+      mbar_wait(&dpt_full[i & 1], (i >> 1) & 1);
       tc_fence_after();
 #pragma unroll
       for (int cc = 0; cc < 2; ++cc) {

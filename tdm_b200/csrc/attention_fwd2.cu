@@ -84,8 +84,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* k_empty = bars + 18;
   uint64_t* v_full = bars + 22;
   uint64_t* v_empty = bars + 26;
-  uint64_t* o_staged = bars + 30;  // [stream]  the item's O tile is in shared memory (the stream's Q buffer)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  // [stream * 2 + item parity]  the item's O tile is in shared memory (the stream's Q buffer).  One barrier per item parity:
+  // a stream needs nothing from the store warp to finish item it+1 (its Q arrived long ago), so on a single barrier a store
+  // warp that is more than one item late would see the awaited parity flip back and wait forever; item it+2 cannot finish
+  // before the store warp has released the Q buffer of item it.
+  uint64_t* o_staged = bars + 30;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kv = (p.Sk + 127) / 128;
@@ -103,7 +107,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one elected arrival per softmax warp of the stream
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_staged[i], 4);
+      mbar_init(&o_staged[2 * i], 4);
+      mbar_init(&o_staged[2 * i + 1], 4);
     }
     for (int i = 0; i < F2_MAX_KS; ++i) {
       mbar_init(&k_full[i], 1);
@@ -171,7 +176,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const int q0 = (item % n_qp) * 256, h = (item / n_qp) % p.H, b = item / (n_qp * p.H);
         for (int s = 0; s < 2; ++s) {
           const int qb = s * 2 + (it & 1);
-          mbar_wait_relaxed(&o_staged[s], it & 1);
+          mbar_wait_relaxed(&o_staged[s * 2 + (it & 1)], (it >> 1) & 1);
           if constexpr (!(DBG & 1)) tma_store_4d(&tmO, sQ + qb * tile_bytes, 0, q0 + s * 128, h, b);  // rows >= Sq are clipped
           tma_store_commit();
           tma_store_wait_read();
@@ -425,7 +430,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (threadIdx.x == 0) F2_TRACE(g - 1, 13);
       fence_async_smem();  // generic-proxy writes -> visible to the TMA store the store warp issues
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_staged[s]);
+      if (lane == 0) mbar_arrive(&o_staged[s * 2 + (it & 1)]);
       if (threadIdx.x == 0) F2_TRACE(g - 1, 14);
     }
   }
