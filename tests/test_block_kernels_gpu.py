@@ -240,3 +240,52 @@ def test_attention_fwd_is_deterministic_with_cold_loads(B, H, S, d):
         else:
             assert torch.equal(o, first_o), f"launch {it}: attention output changed"
             assert torch.equal(lse, first_lse)
+
+
+def test_attention_fwd_bwd_two_streams_many_launches():
+    """Barrier-protocol regression (a protocol bug traps after a bounded wait and surfaces as a launch failure): forward +
+    backward, self + cross, on two streams at once, L2 flushed now and then.  Two hazards of this kind were found by a
+    benchmark run, not by the single-launch tests: a barrier whose producer can run two phases ahead of a waiter needs one
+    instance per phase parity (attn_bwd dpt_full, attn_fwd2 o_staged)."""
+    from tdm_b200 import ops
+    torch.manual_seed(9)
+    B, H, S, L, d = 4, 16, 1024, 120, 72
+    D = H * d
+
+    def make(cross):
+        if not cross:
+            qkv = torch.randn(B, S, 3 * D, device="cuda").bfloat16()
+            q, k, v = (qkv[:, :, i * D:(i + 1) * D].view(B, S, H, d) for i in range(3))
+            dqkv = torch.zeros(B, S, 3 * D, device="cuda", dtype=torch.bfloat16)
+            dq, dk, dv = (dqkv[:, :, i * D:(i + 1) * D].view(B, S, H, d) for i in range(3))
+            bias = None
+        else:
+            q = torch.randn(B, S, H, d, device="cuda").bfloat16()
+            kv = torch.randn(B, L, 2 * D, device="cuda").bfloat16()
+            k, v = kv[:, :, :D].view(B, L, H, d), kv[:, :, D:].view(B, L, H, d)
+            dq = torch.zeros(B, S, H, d, device="cuda", dtype=torch.bfloat16)
+            dkv = torch.zeros(B, L, 2 * D, device="cuda", dtype=torch.bfloat16)
+            dk, dv = dkv[:, :, :D].view(B, L, H, d), dkv[:, :, D:].view(B, L, H, d)
+            bias = torch.zeros(B, L, device="cuda")
+        o = torch.empty(B, S, H, d, device="cuda", dtype=torch.bfloat16)
+        return q, k, v, o, torch.empty(B, H, S, device="cuda"), torch.randn_like(o), dq, dk, dv, bias
+
+    sets = [[make(False), make(True)] for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    junk = torch.empty(160 << 20, device="cuda", dtype=torch.uint8)
+    torch.cuda.synchronize()
+    first = None
+    for it in range(150):
+        for st, cases in zip(streams, sets):
+            with torch.cuda.stream(st):
+                for (q, k, v, o, lse, do, dq, dk, dv, bias) in cases:
+                    ops.attn_fwd(q, k, v, o, d ** -0.5, bias=bias, lse=lse)
+                    ops.attn_bwd(q, k, v, o, do, lse, d ** -0.5, dq, dk, dv, bias=bias)
+        if it % 5 == 0:
+            junk.zero_()
+        if it == 0:
+            torch.cuda.synchronize()
+            first = [c[7].clone() for c in sets[0]]   # dK of both cases: no atomics on that path
+    torch.cuda.synchronize()
+    for c, f in zip(sets[0], first):
+        assert torch.equal(c[7], f), "dK changed between identical launches"
