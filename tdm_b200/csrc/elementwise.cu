@@ -4,6 +4,7 @@
 // warp shuffles; none of them reshapes work into a GEMM.
 // Reference semantics: SURVEY.md Appendix A (diffusers BasicTransformerBlock, ada_norm_single).
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tdm {
@@ -114,6 +115,78 @@ __global__ void __launch_bounds__(256) ln_modulate_fwd_kernel(const float* __res
         w.y = pack_bf16((v[i].z - mean) * rstd * (1.f + b.z) + a.z, (v[i].w - mean) * rstd * (1.f + b.w) + a.w);
         o[i * 32 + lane] = w;
       }
+  }
+}
+
+// Streaming form of the kernel above for the shapes of the model (rows_per_sample % 32 == 0): one CTA per 32 consecutive
+// rows -- ONE wave of resident CTAs for 8192 rows, no tail -- each warp walks its four rows with the NEXT row's loads in
+// flight while the current one is reduced and written, the sample's shift / (1 + scale) rows staged once per CTA.  (The
+// one-row-per-warp grid above runs 1024 CTAs in 2.3 waves of 444: 13.5-15 us for 56.6 MB = 0.58 of the measured copy
+// bandwidth; the ramp and the last, 30 %-full wave are what this form removes.)
+template <int NV>
+__global__ void __launch_bounds__(256, 2) ln_modulate_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ shift,
+                                                                      const float* __restrict__ scale, long mod_stride,
+                                                                      int rows_per_sample, bf16* __restrict__ out,
+                                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                      int M, float eps) {
+  constexpr int D = NV * 128;
+  constexpr int RPW = 4;  // rows per warp
+  __shared__ float4 s_mod[2 * NV * 32];  // shift, then 1 + scale
+  pdl_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_cta = blockIdx.x * 32;
+  const int row0 = row_cta + warp * RPW;
+  float4 v[NV], nx[NV];
+  auto load_row = [&](float4* dst, int row) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (long)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) dst[i] = xr[i * 32 + lane];
+  };
+  if (row0 < M) load_row(v, row0);
+  {  // the CTA's 32 rows belong to one sample
+    const long mb = (long)(row_cta / rows_per_sample) * mod_stride;
+    const float4* sh = reinterpret_cast<const float4*>(shift + mb);
+    const float4* sc = reinterpret_cast<const float4*>(scale + mb);
+    for (int i = threadIdx.x; i < NV * 32; i += 256) {
+      const float4 a = sh[i], b = sc[i];
+      s_mod[i] = a;
+      s_mod[NV * 32 + i] = make_float4(1.f + b.x, 1.f + b.y, 1.f + b.z, 1.f + b.w);
+    }
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int r = 0; r < RPW; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    if (r + 1 < RPW && row + 1 < M) load_row(nx, row + 1);  // in flight under this row's reductions and stores
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+    uint2* o = reinterpret_cast<uint2*>(out + (long)row * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = s_mod[i * 32 + lane], b = s_mod[NV * 32 + i * 32 + lane];
+      uint2 w;
+      w.x = pack_bf16((v[i].x - mean) * rstd * b.x + a.x, (v[i].y - mean) * rstd * b.y + a.y);
+      w.y = pack_bf16((v[i].z - mean) * rstd * b.z + a.z, (v[i].w - mean) * rstd * b.w + a.w);
+      o[i * 32 + lane] = w;
+    }
+    if (r + 1 < RPW) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = nx[i];
+    }
   }
 }
 
@@ -407,6 +480,19 @@ extern "C" int tdm_ln_modulate_fwd(const float* x, const float* shift, const flo
   TDM_REQUIRE(D % 128 == 0 && D <= 128 * LN_MAXV, "tdm_ln_modulate_fwd: D=%d must be a multiple of 128 and <= %d", D, 128 * LN_MAXV);
   TDM_REQUIRE(M > 0 && rows_per_sample > 0 && mod_stride % 4 == 0, "tdm_ln_modulate_fwd: bad shape");
   ::tdm::count_launch();
+  // model shapes: the streaming form (TDM_B200_LN_STREAM=0 keeps the one-row-per-warp grid for A/B timing)
+  const bool no_stream = getenv("TDM_B200_LN_STREAM") && atoi(getenv("TDM_B200_LN_STREAM")) == 0;
+  if (!no_stream && rows_per_sample % 32 == 0 && (D == 1152 || D == 256)) {
+    const int grid = (M + 31) / 32;
+    if (D == 1152)
+      TDM_CHECK_CUDA(launch_pdl(ln_modulate_fwd_stream_kernel<9>, dim3(grid), dim3(256), (size_t)0, (cudaStream_t)stream, x, shift, scale,
+                                (long)mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, eps));
+    else
+      TDM_CHECK_CUDA(launch_pdl(ln_modulate_fwd_stream_kernel<2>, dim3(grid), dim3(256), (size_t)0, (cudaStream_t)stream, x, shift, scale,
+                                (long)mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, eps));
+    TDM_CHECK_CUDA(cudaGetLastError());
+    return TDM_OK;
+  }
 #define TDM_LN_FWD(NVV) TDM_CHECK_CUDA(launch_pdl(ln_modulate_fwd_kernel<NVV>, dim3((M + 7) / 8), dim3(256), (size_t)(2 * D * 4), (cudaStream_t)stream, \
       x, shift, scale, (long)mod_stride, rows_per_sample, (bf16*)out_bf16, mean, rstd, M, D, eps))
   switch (D >> 7) {
