@@ -29,7 +29,10 @@
 //     neither is the limit -- 19 % of all warp samples sit in the softmax warps' wait for S, the rest is spread over
 //     long-scoreboard / fixed-latency stalls of ~700 instructions per warp and tile);
 //   * two warpgroups per stream, thread == half a row, maxima exchanged through shared memory (16 softmax warps, 96
-//     registers): 122 us.
+//     registers): 122 us;
+//   * stream 1 started 1000-2600 clk behind stream 0 at every item (so that one stream's exponentials run under the
+//     other's hand-offs instead of both at once): 75.9-76.5 us against 76.6 -- the phases of the two streams are not what
+//     limits the cycle.
 // What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
 // load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
 // ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us).
