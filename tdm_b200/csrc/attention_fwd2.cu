@@ -142,6 +142,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         for (int s = 0; s < 2; ++s) {
           const int qb = s * 2 + (it & 1);
           mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          if (s == 0) F2_TRACE(it * n_kv, 15);
           mbar_arrive_expect_tx(&q_full[qb], tile_bytes);
           for (int c = 0; c < p.nc; ++c) tma_load_4d(sQ + qb * tile_bytes + c * F2_CH, &tmQ, &q_full[qb], c * 32, q0 + s * 128, h, b);
         }
@@ -269,6 +270,17 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float LOG2E = 1.4426950408889634f;
     const float sc = p.scale_log2;
     int g = 0;
+    // bias value of key (tile * 128 + row) of batch b_: loaded one tile AHEAD into a register (the global-memory round
+    // trip sat between the epilogue of an item and its successor's first tile: ~1000 clk of a ~9800 clk cross-attention item)
+    auto bias_of = [&](int b_, int j_) {
+      const int kv = j_ * 128 + row;
+      float bv = 0.f;
+      if (kv >= p.Sk) bv = -INFINITY;
+      else if (p.bias) bv = p.bias[(long)b_ * p.Sk + kv] * LOG2E;
+      return bv;
+    };
+    float bias_next = 0.f;
+    if (my_items > 0) bias_next = bias_of((int)blockIdx.x / (n_qp * p.H), 0);
     for (int it = 0; it < my_items; ++it) {
       const int item = (int)blockIdx.x + it * (int)gridDim.x;
       const int q0 = (item % n_qp) * 256 + s * 128, h = (item / n_qp) % p.H, b = item / (n_qp * p.H);
@@ -277,13 +289,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const bool need_bias = p.bias != nullptr || (j + 1) * 128 > p.Sk;  // CTA-uniform
         const uint32_t bs_addr = smem_u32(bias_s + (g & 1) * 128);
         if (need_bias) {  // additive key bias (times log2 e) and the key-padding mask of a ragged last tile
-          const int kv = j * 128 + row;
-          float bv = 0.f;
-          if (kv >= p.Sk) bv = -INFINITY;
-          else if (p.bias) bv = p.bias[(long)b * p.Sk + kv] * LOG2E;
-          bias_s[(g & 1) * 128 + row] = bv;
+          bias_s[(g & 1) * 128 + row] = bias_next;
           if (s == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
           else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        {  // the next tile's value (this item's next key tile, or the first one of the next item)
+          const bool last_j = j + 1 == n_kv;
+          const int nb = last_j ? ((int)blockIdx.x + (it + 1) * (int)gridDim.x) / (n_qp * p.H) : b;
+          if (!last_j || it + 1 < my_items) bias_next = bias_of(nb, last_j ? 0 : j + 1);
         }
         mbar_wait(&s_full[s], g & 1);
         tc_fence_after();
@@ -519,13 +532,13 @@ int launch_attn_fwd2(const TdmAttn* a, void* stream) {
     TDM_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     TDM_CHECK_CUDA(cudaMemcpy(host, p.trace, sizeof(host), cudaMemcpyDeviceToHost));
     if (FILE* f = fopen(trace_path, "a")) {
-      fprintf(f, "# fwd2 Sq=%d Sk=%d d=%d events: 0/1 qk_issue s0/s1  2/3 pv_issue s0/s1  4/5 s_full seen  6/7 max done  8/9 p_arrive\n",
+      fprintf(f, "# fwd2 Sq=%d Sk=%d d=%d events: 0/1 qk_issue s0/s1  2/3 pv_issue s0/s1  4/5 s_full seen  6/7 max done  8/9 p_arrive  10-14 epilogue s0  15 Q load issued (item)\n",
               a->Sq, a->Sk, a->d);
       long long t0 = host[0];
       for (int g = 0; g < F2_TRACE_TILES; ++g) {
         if (!host[g * 16 + 4]) break;
         fprintf(f, "%d", g);
-        for (int e = 0; e < 15; ++e) fprintf(f, " %lld", host[g * 16 + e] ? host[g * 16 + e] - t0 : -1);
+        for (int e = 0; e < 16; ++e) fprintf(f, " %lld", host[g * 16 + e] ? host[g * 16 + e] - t0 : -1);
         fprintf(f, "\n");
       }
       fclose(f);
