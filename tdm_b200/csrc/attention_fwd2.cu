@@ -32,7 +32,9 @@
 //     registers): 122 us;
 //   * stream 1 started 1000-2600 clk behind stream 0 at every item (so that one stream's exponentials run under the
 //     other's hand-offs instead of both at once): 75.9-76.5 us against 76.6 -- the phases of the two streams are not what
-//     limits the cycle.
+//     limits the cycle;
+//   * the item's epilogue moved between the two passes of the next item's first tile (hides the wait for the last P V)
+//     with all of O in one tcgen05.ld round: 86.8 us -- the inlined epilogue's 96 registers spill the hot loop.
 // What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
 // load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
 // ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us).
