@@ -34,7 +34,9 @@
 //     other's hand-offs instead of both at once): 75.9-76.5 us against 76.6 -- the phases of the two streams are not what
 //     limits the cycle;
 //   * the item's epilogue moved between the two passes of the next item's first tile (hides the wait for the last P V)
-//     with all of O in one tcgen05.ld round: 86.8 us -- the inlined epilogue's 96 registers spill the hot loop.
+//     with all of O in one tcgen05.ld round: 86.8 us -- the inlined epilogue's 96 registers spill the hot loop;
+//   * both passes as four 32-column chunks with the next chunk's tcgen05.ld in flight under the current one's math (no
+//     spills, 64 live registers as here, but four tcgen05.wait::ld per pass instead of two): 81.6 us.
 // What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
 // load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
 // ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us).
