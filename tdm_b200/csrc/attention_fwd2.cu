@@ -133,6 +133,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_S = tmem_base;        // stream s: + 128 s
   const uint32_t tmem_O = tmem_base + 256;  // stream s: + 128 s
   pdl_sync();
+  if (warp >= 8) {
+  setmaxnreg_dec<104>();
   if (warp == 8) {
     // ===================== TMA producer: Q (both streams) + K =====================
     if (lane == 0) {
@@ -263,7 +265,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (++p_st == KS) { p_st = 0; p_ph ^= 1; }
     }
 #undef F2_ISSUE_QK
+  }
   } else {
+    setmaxnreg_inc<200>();
     // ===================== softmax / correction / epilogue: warpgroup s owns stream s, thread == query row ==========
     const int s = warp >> 2;
     const int row = threadIdx.x & 127;
