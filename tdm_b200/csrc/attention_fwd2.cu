@@ -45,7 +45,7 @@
 
 namespace tdm {
 
-constexpr int F2_THREADS = 384;    // 2 x 4 softmax warps + Q/K TMA warp + MMA warp + V TMA warp + O store warp
+constexpr int F2_THREADS = 384;    // 2 x 4 softmax warps (200 registers each via setmaxnreg) + Q/K TMA warp + MMA warp + V TMA warp + O store warp (104)
 constexpr int F2_CH = 128 * 64;    // one [128 rows x 32 bf16] chunk, 64-byte swizzle
 constexpr int F2_MAX_KS = 4;
 
@@ -315,12 +315,30 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         //      row resident with the other half re-read under the first half's exponentials measured 86-90 us against
         //      74 us for this form -- the register pressure costs more than the extra tcgen05.ld round trips. ----
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          tmem_ld32(s_addr + half * 64, a);
-          tmem_ld32(s_addr + half * 64 + 32, c);
+        if (!need_bias) {
+          // the maximum pass holds nothing but the row: all 128 columns in ONE round trip (128 live registers: the softmax
+          // warpgroups have 200 through setmaxnreg).  The same idea in pass 2 -- second half in flight under the first
+          // half's exponentials -- measured 83 us against 73.5: loads in flight while the warp computes were slower in
+          // every form tried.
+          uint32_t a2[32], c2[32];
+          tmem_ld32(s_addr, a);
+          tmem_ld32(s_addr + 32, c);
+          tmem_ld32(s_addr + 64, a2);
+          tmem_ld32(s_addr + 96, c2);
           tmem_ld_wait();
-          if (need_bias) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, fmaxf(fmaxf(__uint_as_float(a[i]), __uint_as_float(c[i])), fmaxf(__uint_as_float(a2[i]), __uint_as_float(c2[i]))));
+            mx1 = fmaxf(mx1, fmaxf(fmaxf(__uint_as_float(a[i + 1]), __uint_as_float(c[i + 1])), fmaxf(__uint_as_float(a2[i + 1]), __uint_as_float(c2[i + 1]))));
+            mx2 = fmaxf(mx2, fmaxf(fmaxf(__uint_as_float(a[i + 2]), __uint_as_float(c[i + 2])), fmaxf(__uint_as_float(a2[i + 2]), __uint_as_float(c2[i + 2]))));
+            mx3 = fmaxf(mx3, fmaxf(fmaxf(__uint_as_float(a[i + 3]), __uint_as_float(c[i + 3])), fmaxf(__uint_as_float(a2[i + 3]), __uint_as_float(c2[i + 3]))));
+          }
+        } else {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            tmem_ld32(s_addr + half * 64, a);
+            tmem_ld32(s_addr + half * 64 + 32, c);
+            tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
               float4 ba, bc;  // volatile: ptxas otherwise hoists every bias load above the first use
@@ -330,14 +348,6 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
               mx1 = fmaxf(mx1, fmaxf(fmaf(__uint_as_float(a[i + 1]), sc, ba.y), fmaf(__uint_as_float(c[i + 1]), sc, bc.y)));
               mx2 = fmaxf(mx2, fmaxf(fmaf(__uint_as_float(a[i + 2]), sc, ba.z), fmaf(__uint_as_float(c[i + 2]), sc, bc.z)));
               mx3 = fmaxf(mx3, fmaxf(fmaf(__uint_as_float(a[i + 3]), sc, ba.w), fmaf(__uint_as_float(c[i + 3]), sc, bc.w)));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(a[i]), __uint_as_float(c[i])));
-              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(a[i + 1]), __uint_as_float(c[i + 1])));
-              mx2 = fmaxf(mx2, fmaxf(__uint_as_float(a[i + 2]), __uint_as_float(c[i + 2])));
-              mx3 = fmaxf(mx3, fmaxf(__uint_as_float(a[i + 3]), __uint_as_float(c[i + 3])));
             }
           }
         }
