@@ -36,10 +36,15 @@
 //   * the item's epilogue moved between the two passes of the next item's first tile (hides the wait for the last P V)
 //     with all of O in one tcgen05.ld round: 86.8 us -- the inlined epilogue's 96 registers spill the hot loop;
 //   * both passes as four 32-column chunks with the next chunk's tcgen05.ld in flight under the current one's math (no
-//     spills, 64 live registers as here, but four tcgen05.wait::ld per pass instead of two): 81.6 us.
+//     spills, 64 live registers as here, but four tcgen05.wait::ld per pass instead of two): 81.6 us;
+//   * with setmaxnreg 200 / 104 (below): the whole row resident from the maximum pass to the exponentials (one tcgen05.ld
+//     round per tile, no spills): 73.5 us, the same as two rounds -- with S in registers the exponential phase still takes
+//     ~1950 clk per tile (128 MUFU.EX2 per thread, two softmax warps per sub-partition: the XU pipe's 2 x 1024 clk).
 // What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
 // load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
-// ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us).
+// ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us), register headroom for the softmax
+// warpgroups (setmaxnreg 200 for them, 104 for the load / issue / store warps, placed at the top of each role's branch --
+// in a common prologue ptxas spilled every role: 76.3 -> 74.0 us, 4096 tokens 266 -> 254 us).
 #include <stdlib.h>
 #include "common.cuh"
 
