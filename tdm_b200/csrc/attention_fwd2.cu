@@ -29,7 +29,7 @@
 //     neither is the limit -- 19 % of all warp samples sit in the softmax warps' wait for S, the rest is spread over
 //     long-scoreboard / fixed-latency stalls of ~700 instructions per warp and tile);
 //   * two warpgroups per stream, thread == half a row, maxima exchanged through shared memory (16 softmax warps, 96
-//     registers): 122 us;
+//     registers, or 104 / 64 with setmaxnreg): 122-128 us -- 3500 clk for a thread's 64 exponentials in the trace;
 //   * stream 1 started 1000-2600 clk behind stream 0 at every item (so that one stream's exponentials run under the
 //     other's hand-offs instead of both at once): 75.9-76.5 us against 76.6 -- the phases of the two streams are not what
 //     limits the cycle;
