@@ -40,6 +40,8 @@
 //   * with setmaxnreg 200 / 104 (below): the whole row resident from the maximum pass to the exponentials (one tcgen05.ld
 //     round per tile, no spills): 73.5 us, the same as two rounds -- with S in registers the exponential phase still takes
 //     ~1950 clk per tile (128 MUFU.EX2 per thread, two softmax warps per sub-partition: the XU pipe's 2 x 1024 clk).
+//   (ex2.approx.ftz.bf16x2, which would halve the XU work, is not a packed instruction on sm_100a: ptxas emits two
+//   MUFU.EX2.BF16 and a PRMT.)
 // What did pay: the O tile leaving through shared memory + ONE TMA store (thread-per-row 16-byte global stores clogged the
 // load/store queue that mbarrier waits and tcgen05.ld share: 83.5 -> 75.5 us), a dedicated store warp (Q buffer released
 // ~600 clk after the epilogue instead of a tile later: cross-attention 27 -> 25 us), register headroom for the softmax
