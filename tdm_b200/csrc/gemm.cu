@@ -1331,7 +1331,11 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
     // a ragged last column tile fetches (and so costs) only its valid part: count it as a fraction of a tile
     const double units = double(mt) * (double(g->N) / b) * sp;
     const double waves = ceil(units / slots - 0.02);
-    return (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.5) / sp;
+    // three epilogue tensors per element (residual in, fp32 + bf16 out: the O projection): the tile is bound by its
+    // epilogue bytes, which scale with the tile width alone, so three rounds of 192-wide tiles beat three rounds of 256
+    // (measured 34.0 vs 37.1 us at 8192 x 1152 x 1152; scripts/bench_gemm_tiles.py)
+    const double epi = (g->res && g->out_f32 && g->out_bf16 && b == 256) ? 1.3 : 1.0;
+    return epi * (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.5) / sp;
   };
   auto allowed = [&](int b, bool pr) {
     if (g->seg_n > 0 && g->seg_n % b != 0) return false;
