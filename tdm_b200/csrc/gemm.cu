@@ -1334,7 +1334,8 @@ extern "C" int tdm_gemm_bf16(const TdmGemm* g, void* stream) {
     // three epilogue tensors per element (residual in, fp32 + bf16 out: the O projection): the tile is bound by its
     // epilogue bytes, which scale with the tile width alone, so three rounds of 192-wide tiles beat three rounds of 256
     // (measured 34.0 vs 37.1 us at 8192 x 1152 x 1152; scripts/bench_gemm_tiles.py)
-    const double epi = (g->res && g->out_f32 && g->out_bf16 && b == 256) ? 1.3 : 1.0;
+    // (the same holds for FF2 -- gate + residual, K = 4608: 84.1 vs 86.5 us -- but not for o2, K = 1152: 29.7 vs 28.7)
+    const double epi = (b == 256 && g->res && g->out_f32 && (g->out_bf16 || (g->gate && g->K >= 4096))) ? 1.3 : 1.0;
     return epi * (pr ? waves * double(b + 128) : waves * double(b + 64) * 1.5) / sp;
   };
   auto allowed = [&](int b, bool pr) {
